@@ -1,0 +1,209 @@
+/*
+ * legion_b200.h -- C-ABI of the B200-native Legion mini-batch hot path.
+ *
+ * Plain C: opaque handles, POD structs, raw pointers + sizes, int status codes
+ * (0 = LGN_OK, negative = error; lgn_error_string() explains).  No torch / C++
+ * types cross this boundary.  Every entry point names the reference interface
+ * it replaces (paths relative to the reference checkout, liayan/Legion-1).
+ *
+ * Pointer conventions: "dev" pointers must be dereferenceable by kernels running
+ * on the context's GPU -- local device memory, peer device memory (P2P enabled or
+ * opened from an IPC handle) or mapped pinned host memory (UVA zero-copy).
+ * All hot-path calls are asynchronous on the caller's stream (a cudaStream_t
+ * passed as void*; NULL = legacy default stream) and never synchronise the host.
+ */
+#ifndef LEGION_B200_H
+#define LEGION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGN_MAX_HOPS 5
+#define LGN_MAX_PARTS 8        /* MAX_DEVICE, CUDA_IPC_Service.cu:16 */
+#define LGN_PIPELINE_DEPTH 2   /* PIPELINE_DEPTH, CUDA_IPC_Service.cu:17 */
+
+enum {
+    LGN_OK = 0,
+    LGN_E_ARG = -1,        /* bad argument */
+    LGN_E_CUDA = -2,       /* CUDA runtime error (see lgn_last_cuda_error) */
+    LGN_E_STATE = -3,      /* call order violated (e.g. gather before features bound) */
+    LGN_E_CAPACITY = -4,   /* batch buffers too small (reference: unchecked, Server.cu:275) */
+    LGN_E_SYS = -5         /* shm / semaphore failure */
+};
+
+enum { LGN_RNG_MINSTD = 0, LGN_RNG_PHILOX = 1 };
+enum { LGN_MODE_TRAIN = 0, LGN_MODE_VALID = 1, LGN_MODE_TEST = 2 };   /* Kernels.cu:10-12 */
+
+const char* lgn_error_string(int code);
+const char* lgn_last_cuda_error(void);
+int lgn_version(void);
+
+/* ------------------------------------------------------------------ memory
+ * replaces d_alloc_space / d_free_space / host_alloc_space / d_copy_2_h /
+ * SetGPUDevice / GetGPUDevice (Kernels.cuh:24-46, Kernels.cu:14-64). */
+int lgn_set_device(int32_t device);
+int lgn_get_device(int32_t* device);
+int lgn_device_count(int32_t* count);
+int lgn_device_alloc(void** dev_ptr, int64_t bytes);
+int lgn_device_free(void* dev_ptr);
+/* pinned + mapped host memory; *dev_alias is the UVA pointer kernels may read. */
+int lgn_host_alloc_mapped(void** host_ptr, void** dev_alias, int64_t bytes);
+int lgn_host_free(void* host_ptr);
+int lgn_copy_h2d(void* dev_dst, const void* host_src, int64_t bytes);
+int lgn_copy_d2h(void* host_dst, const void* dev_src, int64_t bytes);
+int lgn_memset_d(void* dev_dst, int value, int64_t bytes);
+/* all-pairs cudaDeviceEnablePeerAccess among the first n devices
+ * (GPUGraphStore::EnableP2PAccess, GPUGraphStore.cu:145-168). */
+int lgn_enable_peer_access(int32_t n_devices);
+/* 64-byte CUDA IPC handles for cross-process peer shards / trainer buffers
+ * (cudaIpcGetMemHandle / cudaIpcOpenMemHandle, CUDA_IPC_Service.cu:169-175,
+ * ipc_cuda_kernel.cu:63-69). */
+int lgn_ipc_export(void* dev_ptr, uint8_t handle[64]);
+int lgn_ipc_import(const uint8_t handle[64], void** dev_ptr);
+int lgn_ipc_close(void* dev_ptr);
+
+/* ------------------------------------------------------------------ context
+ * One context per GPU = the reference's GPURunner + its GPUMemoryPool
+ * (Server.cu:167-364, GPUMemoryPool.cuh:7-208). */
+typedef struct lgn_ctx lgn_ctx;
+
+typedef struct {
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t part;                   /* this GPU's index inside the NVLink clique (0..n_parts-1) */
+    int64_t n_nodes;                /* N */
+    int32_t feat_dim;               /* D (floats per row) */
+    int32_t batch_size;             /* raw batch size B (meta_config field 2) */
+    int32_t n_hops;                 /* reference: 2 (Server.cu:68-69) */
+    int32_t fanout[LGN_MAX_HOPS];   /* reference: {25,10} */
+    int32_t rng_mode;               /* LGN_RNG_* */
+    uint64_t rng_seed;              /* philox key */
+    int64_t max_feature_rows;       /* 0 = worst case B*(1+f1+f1*f2+..); reference: 1.2*max presampled ids */
+    int32_t enable_hotness;         /* allocate the two u32[N] presampling histograms */
+    int32_t reserved;
+} lgn_config;
+
+int lgn_create(const lgn_config* cfg, lgn_ctx** out);
+int lgn_destroy(lgn_ctx* ctx);
+/* B*(1+f1+f1*f2+...) : per-pipe id / edge buffer capacity (Server.cu:184-196). */
+int64_t lgn_capacity(const lgn_ctx* ctx);
+
+/* ------------------------------------------------------------------ storage
+ * replaces GPUNodeStorage / GPUGraphStorage pointer tables
+ * (GPU_Node_Storage.cuh:24-58, GPU_Graph_Storage.cuh:20-37). */
+/* per-mode seed lists of this GPU's partition (GPU_Memory_Node_Storage.cu:52-94) */
+int lgn_bind_seeds(lgn_ctx* ctx, int32_t mode, const int32_t* ids_dev, const int32_t* labels_dev, int32_t count);
+/* base CSR = slot [partition_count] of the reference tables: the full graph,
+ * normally the mapped-host copy (GPU_Memory_Graph_Storage.cu:86-93). */
+int lgn_bind_topology(lgn_ctx* ctx, const int64_t* indptr_dev, const int32_t* indices_dev);
+/* topology cache shards: slot_of[id] = part*cap + row or -1 (replaces the two
+ * cuckoo maps of FindTopo, GPUCache.cu:434-443); NULL slot_of disables it. */
+int lgn_bind_topology_cache(lgn_ctx* ctx, int32_t n_parts, const int64_t* const* indptr_tab,
+                            const int32_t* const* indices_tab, const int32_t* slot_of_dev, int64_t cap);
+/* base feature matrix float32[N,D] (mapped host, GPU_Memory_Node_Storage.cu:22-24) */
+int lgn_bind_features(lgn_ctx* ctx, const float* features_dev);
+/* feature cache shards: slot_of[id] = part*cap + row or -1 (replaces FindFeat's
+ * cuckoo map, GPUCache.cu:387-432); shard_tab = Global_Float_Feature_Cache. */
+int lgn_bind_feature_cache(lgn_ctx* ctx, int32_t n_parts, const float* const* shard_tab,
+                           const int32_t* slot_of_dev, int64_t cap);
+
+/* ------------------------------------------------------------------ hot path
+ * One call per reference operator (Operator.cu:10-123); all asynchronous. */
+/* op 0: batch_generator_kernel (Kernels.cu:163-232). Selects the pipe slot. */
+int lgn_batch_generate(lgn_ctx* ctx, void* stream, int32_t pipe, int32_t mode, int32_t batch_size, int32_t counter);
+/* same, seeds supplied by the caller from (pinned) host memory: H2D inside. */
+int lgn_batch_from_host(lgn_ctx* ctx, void* stream, int32_t pipe, const int32_t* seeds_host,
+                        const int32_t* labels_host, int32_t count, uint32_t step);
+/* ops 2,4,..: GPU_Random_Sampling (Kernels.cu:567-659) for hop = 0..n_hops-1.
+ * is_presc: read the base CSR only and count topology hotness (Kernels.cu:468-564). */
+int lgn_sample_hop(lgn_ctx* ctx, void* stream, int32_t hop, int32_t is_presc);
+/* ops 1,3,5,..: get_feature_kernel (Kernels.cu:707-748) for segment = 0..n_hops. */
+int lgn_gather_segment(lgn_ctx* ctx, void* stream, int32_t segment);
+/* op 6/7: make_update_plan / update_cache (Kernels.cu:759-805): node hotness when
+ * is_presc (HotnessMeasure, GPUCache.cu:227-235) and scratch reset (ClearPosMap). */
+int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);
+/* the whole GPURunner::RunOnce / RunPreSc DAG (Server.cu:284-328) on one stream pair:
+ * sampling on `stream`, gathers on the context's second stream, joined at the end. */
+int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_presc);
+
+/* ------------------------------------------------------------------ results */
+typedef struct {
+    int32_t* ids;           /* int32[capacity]   sampled_ids  (IPC handle 0) */
+    float* features;        /* f32[max_rows, D]               (IPC handle 1) */
+    int32_t* labels;        /* int32[B]                       (IPC handle 2) */
+    int32_t* agg_src;       /* int32[capacity]   local index of sampled neighbour (IPC handle 3) */
+    int32_t* agg_dst;       /* int32[capacity]   local index of frontier node     (IPC handle 4) */
+    int32_t* node_counter;  /* int32[16]                      (IPC handle 5) */
+    int32_t* edge_counter;  /* int32[16]                      (IPC handle 6) */
+    int32_t* agg_src_ids;   /* raw ids (GPUMemoryPool::GetAggSrcId), shared between pipes */
+    int32_t* agg_dst_ids;   /* raw ids (GPUMemoryPool::GetAggDstId) */
+    int64_t capacity;
+    int64_t max_rows;
+} lgn_batch_view;
+int lgn_batch_buffers(lgn_ctx* ctx, int32_t pipe, lgn_batch_view* out);
+/* D2H of both counter blocks on `stream` + stream sync: what ipc_service.get_next
+ * does on the trainer side (ipc_cuda_kernel.cu:192-193). */
+int lgn_read_counters(lgn_ctx* ctx, void* stream, int32_t pipe, int32_t nc[16], int32_t ec[16]);
+/* rows served per tier by the gathers since the last reset: [local, peer, host] */
+int lgn_tier_counts(lgn_ctx* ctx, void* stream, int64_t out[3], int32_t reset);
+/* sticky device-side status: 0 or LGN_E_CAPACITY */
+int lgn_status(lgn_ctx* ctx, void* stream);
+
+/* ------------------------------------------------------------------ planner
+ * presampling statistics and cache construction (GPUCache.cu:578-826). */
+int lgn_hotness(lgn_ctx* ctx, uint32_t** node_hotness_dev, uint32_t** topo_hotness_dev);
+int32_t lgn_max_ids(lgn_ctx* ctx, void* stream);  /* PreSCCacheController::MaxIdNum (GPUCache.cu:294-296) */
+/* order[i] = id of rank i under (count desc, id asc): CandidateSelection's
+ * sort_by_key (GPUCache.cu:630-631). sorted_counts may be NULL. */
+int lgn_hot_order(const uint32_t* counts_dev, int64_t n, int32_t* order_dev, uint32_t* sorted_counts_dev, void* stream);
+/* slot_of[id] = (i%kg)*cap + i/kg for rank i < min(cap*kg, n) else -1 (InitPair, GPUCache.cu:103-108) */
+int lgn_place(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t* slot_of_dev, void* stream);
+/* shard j row r <- features[order[r*kg+j]] (FeatFillUp, GPUCache.cu:200-205) */
+int lgn_fill_feature_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j,
+                           const float* features_dev, int32_t dim, float* shard_dev, void* stream);
+/* topology shard j (GraphCache, GPU_Memory_Graph_Storage.cu:98-133). Pass
+ * indices_out_dev = NULL to size it: *n_indices receives the count (host sync). */
+int lgn_fill_topo_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j,
+                        const int64_t* indptr_dev, const int32_t* indices_dev,
+                        int64_t* indptr_out_dev, int32_t* indices_out_dev, int64_t* n_indices, void* stream);
+/* CostModel (GPUCache.cu:661-767); sorted counts / order are device arrays. */
+int lgn_cost_model(const uint32_t* af_sorted_dev, const uint32_t* at_sorted_dev, const int32_t* qt_dev,
+                   const int64_t* indptr_dev, int64_t n, int32_t dim, int64_t cache_memory, int32_t kg,
+                   uint64_t topo_trans, const int32_t* max_ids, int32_t train_step,
+                   int32_t* node_capacity, int32_t* edge_capacity);
+
+/* ------------------------------------------------------------------ IPC wire format
+ * server side of CUDA_IPC_Service (CUDA_IPC_Service.cu:34-359): POSIX shm
+ * "simpleIPCshm" {int32 steps[3]; handle[8][2][7]}, sems sem_r_/sem_w_<dev>_<pipe>. */
+typedef struct lgn_ipc_server lgn_ipc_server;
+int lgn_ipc_server_create(int32_t n_devices, const int32_t steps[3], lgn_ipc_server** out);
+int lgn_ipc_server_publish(lgn_ipc_server* s, int32_t device, lgn_ctx* ctx, int32_t with_features);
+int lgn_ipc_server_wait(lgn_ipc_server* s, int32_t device, int32_t pipe);   /* IPCWait  (sem_r) */
+int lgn_ipc_server_post(lgn_ipc_server* s, int32_t device, int32_t pipe);   /* IPCPost  (sem_w) */
+int lgn_ipc_server_destroy(lgn_ipc_server* s);
+/* trainer side (pytorch_extension/ipc_cuda_kernel.cu:38-176) */
+typedef struct lgn_ipc_client lgn_ipc_client;
+int lgn_ipc_client_open(int32_t device, lgn_ipc_client** out);
+int lgn_ipc_client_steps(lgn_ipc_client* c, int32_t steps[3]);
+/* Wait() + counter D2H; fills the 7 device pointers of the current pipe */
+int lgn_ipc_client_next(lgn_ipc_client* c, void* ptrs[7], int32_t nc[16], int32_t ec[16]);
+int lgn_ipc_client_release(lgn_ipc_client* c);                              /* Post() + pipe flip */
+int lgn_ipc_client_close(lgn_ipc_client* c);
+
+/* step arithmetic of IPCEnv::Coordinate / GetCurrentMode / GetLocalBatchId
+ * (CUDA_IPC_Service.cu:66-134, 219-259). */
+typedef struct {
+    int32_t train_step, valid_step, test_step, max_step;
+    int32_t valid_batch[LGN_MAX_PARTS], test_batch[LGN_MAX_PARTS];
+} lgn_steps;
+int lgn_coordinate(const int32_t* n_train, const int32_t* n_valid, const int32_t* n_test, int32_t parts,
+                   int32_t batch, int32_t epochs, lgn_steps* out);
+int32_t lgn_mode_of_step(const lgn_steps* s, int32_t epochs, int32_t global_batch_id);
+int32_t lgn_local_batch_id(const lgn_steps* s, int32_t epochs, int32_t global_batch_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

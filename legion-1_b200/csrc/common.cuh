@@ -1,0 +1,109 @@
+// common.cuh -- shared device helpers for the sm_100a Legion hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/legion_b200.h"
+
+namespace lgn {
+
+// ---- slot_map encoding -------------------------------------------------
+// One int32 per node replaces the reference's dedup bitmap + position_map
+// (Kernels.cu:88-92, 412-438).  value < CAND  : final local index of the node
+//                               CAND + slot   : smallest slot that sampled it this hop
+//                               EMPTY         : not in the current batch
+constexpr int32_t EMPTY = 0x7fffffff;
+constexpr int32_t CAND = 0x40000000;
+
+// ---- per-batch device state (written by kernels, never read by the host on
+// the hot path) ----------------------------------------------------------
+struct HopState {
+    int32_t n_items;     // frontier size F of this hop (nc[2])
+    int32_t item_base;   // offset of the frontier inside agg_src_ids (ec[2]); hop 0: seeds
+    int32_t node_base;   // write cursor into sampled_ids (nc[0])
+    int32_t edge_base;   // write cursor into the agg arrays (ec[0])
+};
+
+struct BatchState {
+    HopState hop[LGN_MAX_HOPS + 1];
+    uint32_t step;          // philox counter word 3 (global batch id)
+    int32_t status;         // sticky: 0 or LGN_E_CAPACITY
+    int32_t max_ids;        // max unique ids over presampled batches (GPUCache.cu:294-296)
+    int32_t pad;
+    unsigned long long tier_rows[4];   // local, peer, host rows gathered
+};
+
+// ---- cache-hinted 128-bit / 32-bit accesses (G13/G14 of the Blackwell guide) ----
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_nc_u32(const void* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cs_v4(void* p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_u32(void* p, uint32_t v)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- thrust::minstd_rand compatibility (Kernels.cu:402-405) ----------------
+// state after discard(z) from seed 1 is 48271^z mod (2^31-1); the next draw is
+// 48271^(z+1).  Mersenne modulus => fold instead of divide.
+__device__ __forceinline__ uint32_t mulmod_m31(uint32_t a, uint32_t b)
+{
+    unsigned long long p = (unsigned long long)a * b;          // < 2^62
+    unsigned long long f = (p & 0x7fffffffull) + (p >> 31);     // < 2^32
+    uint32_t r = (uint32_t)(f & 0x7fffffffull) + (uint32_t)(f >> 31);
+    return r >= 0x7fffffffu ? r - 0x7fffffffu : r;
+}
+__device__ __forceinline__ uint32_t minstd_pow(unsigned long long e)
+{
+    uint32_t base = 48271u, acc = 1u;
+    while (e) {
+        if (e & 1ull) acc = mulmod_m31(acc, base);
+        e >>= 1;
+        base = mulmod_m31(base, base);
+    }
+    return acc;
+}
+// uniform_int_distribution<int>(0, deg-1) on top of the raw draw x (thrust
+// uniform_real_distribution.inl: double(x-min)/(1+double(max-min)) * deg).
+__device__ __forceinline__ int32_t minstd_to_pick(uint32_t x, int32_t deg)
+{
+    double u = (double)(x - 1u);
+    u = __ddiv_rn(u, 2147483646.0);
+    return (int32_t)__dmul_rn(u, (double)deg);
+}
+
+// ---- Philox4x32-10, counter = (slot_lo, slot_hi, hop, step), key = seed ----
+__device__ __forceinline__ uint32_t philox_first_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                      uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+__device__ __forceinline__ int32_t philox_pick(unsigned long long idx, uint32_t hop, uint32_t step,
+                                               unsigned long long seed, int32_t deg)
+{
+    uint32_t r = philox_first_word((uint32_t)idx, (uint32_t)(idx >> 32), hop, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (int32_t)__umulhi(r, (uint32_t)deg);
+}
+
+}  // namespace lgn

@@ -1,0 +1,425 @@
+// context.cu -- C-ABI entry points: memory helpers, per-GPU context, storage binding and
+// the operator calls (include/legion_b200.h).  Host logic mirrors GPURunner
+// (Server.cu:167-364) and the extern "C" wrappers of Kernels.cu without their blocking
+// cudaMemcpy / malloc on the hot loop (Kernels.cu:605-625, GPUCache.cu:394-395).
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "context.h"
+
+thread_local char g_lgn_cuda_err[256] = "";
+
+int lgn_cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_lgn_cuda_err, sizeof(g_lgn_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return LGN_E_CUDA;
+}
+#define CK(x)                                                 \
+    do {                                                      \
+        cudaError_t e_ = (x);                                 \
+        if (e_ != cudaSuccess) return lgn_cuda_fail(e_, #x);  \
+    } while (0)
+
+using namespace lgn;
+
+extern "C" {
+
+const char* lgn_error_string(int code)
+{
+    switch (code) {
+        case LGN_OK: return "ok";
+        case LGN_E_ARG: return "invalid argument";
+        case LGN_E_CUDA: return "CUDA error";
+        case LGN_E_STATE: return "invalid call order / missing binding";
+        case LGN_E_CAPACITY: return "batch buffer capacity exceeded";
+        case LGN_E_SYS: return "system (shm/semaphore) error";
+    }
+    return "unknown";
+}
+const char* lgn_last_cuda_error(void) { return g_lgn_cuda_err; }
+int lgn_version(void) { return 100; }
+
+// ---------------------------------------------------------------- memory
+int lgn_set_device(int32_t d) { CK(cudaSetDevice(d)); return LGN_OK; }
+int lgn_get_device(int32_t* d) { int x = 0; CK(cudaGetDevice(&x)); *d = x; return LGN_OK; }
+int lgn_device_count(int32_t* n) { int x = 0; CK(cudaGetDeviceCount(&x)); *n = x; return LGN_OK; }
+int lgn_device_alloc(void** p, int64_t bytes) { if (!p || bytes < 0) return LGN_E_ARG; CK(cudaMalloc(p, (size_t)(bytes > 0 ? bytes : 1))); return LGN_OK; }
+int lgn_device_free(void* p) { CK(cudaFree(p)); return LGN_OK; }
+int lgn_host_alloc_mapped(void** host, void** dev, int64_t bytes)
+{
+    if (!host || !dev || bytes < 0) return LGN_E_ARG;
+    CK(cudaHostAlloc(host, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocMapped | cudaHostAllocPortable));   // Kernels.cu:57-64
+    CK(cudaHostGetDevicePointer(dev, *host, 0));
+    return LGN_OK;
+}
+int lgn_host_free(void* host) { CK(cudaFreeHost(host)); return LGN_OK; }
+int lgn_copy_h2d(void* d, const void* h, int64_t bytes) { CK(cudaMemcpy(d, h, (size_t)bytes, cudaMemcpyHostToDevice)); return LGN_OK; }
+int lgn_copy_d2h(void* h, const void* d, int64_t bytes) { CK(cudaMemcpy(h, d, (size_t)bytes, cudaMemcpyDeviceToHost)); return LGN_OK; }
+int lgn_memset_d(void* d, int v, int64_t bytes) { CK(cudaMemset(d, v, (size_t)bytes)); return LGN_OK; }
+
+int lgn_enable_peer_access(int32_t n)
+{
+    int cur = 0;
+    CK(cudaGetDevice(&cur));
+    for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(i));
+        for (int j = 0; j < n; j++) {
+            if (i == j) continue;
+            int ok = 0;
+            CK(cudaDeviceCanAccessPeer(&ok, i, j));
+            if (ok) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return lgn_cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            }
+        }
+    }
+    CK(cudaSetDevice(cur));
+    return LGN_OK;
+}
+
+int lgn_ipc_export(void* p, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "wire format assumes 64-byte handles");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, 64);
+    return LGN_OK;
+}
+int lgn_ipc_import(const uint8_t handle[64], void** p)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return LGN_OK;
+}
+int lgn_ipc_close(void* p) { CK(cudaIpcCloseMemHandle(p)); return LGN_OK; }
+
+// ---------------------------------------------------------------- context
+static int fill_i32(int32_t* p, int32_t v, long long n, cudaStream_t s);
+
+__global__ void k_fill_i32(int32_t* p, int32_t v, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+static int fill_i32(int32_t* p, int32_t v, long long n, cudaStream_t s)
+{
+    k_fill_i32<<<1024, 256, 0, s>>>(p, v, n);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_create(const lgn_config* cfg, lgn_ctx** out)
+{
+    if (!cfg || !out) return LGN_E_ARG;
+    if (cfg->n_nodes <= 0 || cfg->n_nodes > 0x7fffffffLL || cfg->feat_dim < 0 || cfg->batch_size <= 0) return LGN_E_ARG;
+    if (cfg->n_hops < 0 || cfg->n_hops > LGN_MAX_HOPS || cfg->part < 0 || cfg->part >= LGN_MAX_PARTS) return LGN_E_ARG;
+    if (cfg->rng_mode != LGN_RNG_MINSTD && cfg->rng_mode != LGN_RNG_PHILOX) return LGN_E_ARG;
+    long long cap = cfg->batch_size, cur = cfg->batch_size, max_slots = 1;
+    for (int h = 0; h < cfg->n_hops; h++) {             // Server.cu:184-196
+        if (cfg->fanout[h] <= 0 || cfg->fanout[h] > 256) return LGN_E_ARG;
+        cur *= cfg->fanout[h];
+        cap += cur;
+        if (cur > max_slots) max_slots = cur;
+        if (cap >= lgn::CAND) return LGN_E_ARG;         // slot indices must stay below the CAND tag
+    }
+    CK(cudaSetDevice(cfg->device));
+    lgn_ctx* c = new (std::nothrow) lgn_ctx();
+    if (!c) return LGN_E_ARG;
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->capacity = cap;
+    c->max_slots = max_slots;
+    c->max_rows = cfg->max_feature_rows > 0 ? cfg->max_feature_rows : cap;
+    CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    for (int p = 0; p < LGN_PIPELINE_DEPTH; p++) {      // CUDA_IPC_Service.cu:140-215
+        lgn::Pipe& pp = c->pipe[p];
+        CK(cudaMalloc(&pp.ids, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.labels, (size_t)cfg->batch_size * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.agg_src_off, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.agg_dst_off, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.nc, 16 * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.ec, 16 * sizeof(int32_t)));
+        CK(cudaMemset(pp.nc, 0, 64));
+        CK(cudaMemset(pp.ec, 0, 64));
+        if (cfg->feat_dim > 0) CK(cudaMalloc(&pp.features, (size_t)c->max_rows * cfg->feat_dim * sizeof(float)));
+    }
+    CK(cudaMalloc(&c->slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));      // Server.cu:219-222
+    CK(cudaMalloc(&c->agg_src_ids, cap * sizeof(int32_t)));
+    CK(cudaMalloc(&c->agg_dst_ids, cap * sizeof(int32_t)));
+    CK(cudaMalloc(&c->slot_dst, (max_slots + 4) * sizeof(int32_t)));
+    const long long n_status = ((max_slots + 1023) / 1024 + 1) * LGN_MAX_HOPS;
+    CK(cudaMalloc(&c->scan_status, n_status * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->scan_ticket, LGN_MAX_HOPS * sizeof(int32_t)));
+    CK(cudaMalloc(&c->state, sizeof(lgn::BatchState)));
+    CK(cudaMemset(c->state, 0, sizeof(lgn::BatchState)));
+    CK(cudaMalloc(&c->seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
+    if (cfg->enable_hotness) {                                                   // GPUCache.cu:256-261 (u64 there)
+        CK(cudaMalloc(&c->node_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+        CK(cudaMalloc(&c->topo_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+        CK(cudaMemset(c->node_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+        CK(cudaMemset(c->topo_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+    }
+    int rc = fill_i32(c->slot_map, lgn::EMPTY, cfg->n_nodes, 0);
+    if (rc) return rc;
+    CK(cudaStreamCreateWithFlags(&c->gather_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&c->ev_hop[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    c->feat.my_part = cfg->part;
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return LGN_OK;
+}
+
+int lgn_destroy(lgn_ctx* c)
+{
+    if (!c) return LGN_E_ARG;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < LGN_PIPELINE_DEPTH; p++) {
+        lgn::Pipe& pp = c->pipe[p];
+        cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
+        cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
+    }
+    cudaFree(c->slot_map); cudaFree(c->agg_src_ids); cudaFree(c->agg_dst_ids); cudaFree(c->slot_dst);
+    cudaFree(c->scan_status); cudaFree(c->scan_ticket); cudaFree(c->state); cudaFree(c->seed_stage);
+    cudaFree(c->node_hotness); cudaFree(c->topo_hotness);
+    cudaStreamDestroy(c->gather_stream);
+    for (int i = 0; i < LGN_MAX_HOPS + 2; i++) cudaEventDestroy(c->ev_hop[i]);
+    cudaEventDestroy(c->ev_join);
+    cudaGetLastError();
+    delete c;
+    return LGN_OK;
+}
+
+int64_t lgn_capacity(const lgn_ctx* c) { return c ? c->capacity : 0; }
+
+// ---------------------------------------------------------------- storage binding
+int lgn_bind_seeds(lgn_ctx* c, int32_t mode, const int32_t* ids, const int32_t* labels, int32_t count)
+{
+    if (!c || mode < 0 || mode > 2 || count < 0 || (count > 0 && !ids)) return LGN_E_ARG;
+    c->seed_ids[mode] = ids; c->seed_labels[mode] = labels; c->seed_count[mode] = count;
+    return LGN_OK;
+}
+int lgn_bind_topology(lgn_ctx* c, const int64_t* indptr, const int32_t* indices)
+{
+    if (!c || !indptr || !indices) return LGN_E_ARG;
+    c->topo.base_indptr = indptr; c->topo.base_indices = indices;
+    return LGN_OK;
+}
+int lgn_bind_topology_cache(lgn_ctx* c, int32_t n_parts, const int64_t* const* indptr_tab, const int32_t* const* indices_tab,
+                            const int32_t* slot_of, int64_t cap)
+{
+    if (!c || n_parts < 0 || n_parts > LGN_MAX_PARTS) return LGN_E_ARG;
+    if (!slot_of || n_parts == 0) { c->topo.slot_of = nullptr; return LGN_OK; }
+    if (cap <= 0 || !indptr_tab || !indices_tab) return LGN_E_ARG;
+    for (int i = 0; i < n_parts; i++) { c->topo.indptr_tab[i] = indptr_tab[i]; c->topo.indices_tab[i] = indices_tab[i]; }
+    c->topo.cap = cap; c->topo.slot_of = slot_of;
+    return LGN_OK;
+}
+int lgn_bind_features(lgn_ctx* c, const float* features)
+{
+    if (!c || !features) return LGN_E_ARG;
+    c->feat.base = features;
+    return LGN_OK;
+}
+int lgn_bind_feature_cache(lgn_ctx* c, int32_t n_parts, const float* const* shard_tab, const int32_t* slot_of, int64_t cap)
+{
+    if (!c || n_parts < 0 || n_parts > LGN_MAX_PARTS) return LGN_E_ARG;
+    if (!slot_of || n_parts == 0) { c->feat.slot_of = nullptr; c->feat.n_parts = 0; return LGN_OK; }
+    if (cap <= 0 || !shard_tab) return LGN_E_ARG;
+    for (int i = 0; i < n_parts; i++) c->feat.shard_tab[i] = shard_tab[i];
+    c->feat.cap = cap; c->feat.slot_of = slot_of; c->feat.n_parts = n_parts;
+    return LGN_OK;
+}
+
+// ---------------------------------------------------------------- hot path
+int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int32_t batch_size, int32_t counter)
+{
+    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH || mode < 0 || mode > 2 || batch_size <= 0 || counter < 0) return LGN_E_ARG;
+    if (batch_size > c->cfg.batch_size) return LGN_E_CAPACITY;
+    if (!c->seed_ids[mode]) return LGN_E_STATE;
+    const int32_t total = c->seed_count[mode];
+    // Kernels.cu:224-227: last batch is clamped, and the kernel strides by the clamped size
+    long long size = ((long long)batch_size * (counter + 1) >= total) ? (long long)total - (long long)batch_size * counter : batch_size;
+    if (size < 0) size = 0;
+    const long long off = size * counter;
+    c->cur_pipe = pipe;
+    launch_batch_begin(c, (cudaStream_t)stream, c->seed_ids[mode], c->seed_labels[mode], (int32_t)off, (int32_t)size, (uint32_t)counter);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_batch_from_host(lgn_ctx* c, void* stream, int32_t pipe, const int32_t* seeds, const int32_t* labels, int32_t count, uint32_t step)
+{
+    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH || count < 0 || (count > 0 && !seeds)) return LGN_E_ARG;
+    if (count > c->cfg.batch_size) return LGN_E_CAPACITY;
+    cudaStream_t s = (cudaStream_t)stream;
+    c->cur_pipe = pipe;
+    if (count > 0) CK(cudaMemcpyAsync(c->seed_stage, seeds, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+    if (count > 0 && labels) CK(cudaMemcpyAsync(c->seed_stage + c->cfg.batch_size, labels, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+    launch_batch_begin(c, s, c->seed_stage, labels ? c->seed_stage + c->cfg.batch_size : nullptr, 0, count, step);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_sample_hop(lgn_ctx* c, void* stream, int32_t hop, int32_t is_presc)
+{
+    if (!c || hop < 0 || hop >= c->cfg.n_hops) return LGN_E_ARG;
+    if (!c->topo.base_indptr) return LGN_E_STATE;
+    if (is_presc && !c->topo_hotness) return LGN_E_STATE;
+    launch_sample_hop(c, (cudaStream_t)stream, hop, is_presc != 0);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_gather_segment(lgn_ctx* c, void* stream, int32_t segment)
+{
+    if (!c || segment < 0 || segment > c->cfg.n_hops) return LGN_E_ARG;
+    if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
+    launch_gather(c, (cudaStream_t)stream, segment);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_finish_batch(lgn_ctx* c, void* stream, int32_t is_presc)
+{
+    if (!c) return LGN_E_ARG;
+    if (is_presc && !c->node_hotness) return LGN_E_STATE;
+    launch_batch_end(c, (cudaStream_t)stream, is_presc != 0);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+// GPURunner::RunOnce / RunPreSc (Server.cu:284-328): sampling ops on `stream`, feature
+// extraction ops on the second stream, chained by events; the caller's stream joins at the end.
+int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_presc)
+{
+    if (!c) return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream, g = c->gather_stream;
+    const bool feats = with_features && !is_presc && c->feat.base && c->cfg.feat_dim > 0;
+    if (with_features && !is_presc && !feats) return LGN_E_STATE;
+    int rc;
+    if (feats) {
+        CK(cudaEventRecord(c->ev_hop[0], s));
+        CK(cudaStreamWaitEvent(g, c->ev_hop[0], 0));
+        if ((rc = lgn_gather_segment(c, g, 0))) return rc;
+    }
+    for (int h = 0; h < c->cfg.n_hops; h++) {
+        if ((rc = lgn_sample_hop(c, s, h, is_presc))) return rc;
+        if (feats) {
+            CK(cudaEventRecord(c->ev_hop[h + 1], s));
+            CK(cudaStreamWaitEvent(g, c->ev_hop[h + 1], 0));
+            if ((rc = lgn_gather_segment(c, g, h + 1))) return rc;
+        }
+    }
+    if ((rc = lgn_finish_batch(c, s, is_presc))) return rc;
+    if (feats) {
+        CK(cudaEventRecord(c->ev_join, g));
+        CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+    }
+    return LGN_OK;
+}
+
+// ---------------------------------------------------------------- results
+int lgn_batch_buffers(lgn_ctx* c, int32_t pipe, lgn_batch_view* v)
+{
+    if (!c || !v || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH) return LGN_E_ARG;
+    const lgn::Pipe& p = c->pipe[pipe];
+    v->ids = p.ids; v->features = p.features; v->labels = p.labels; v->agg_src = p.agg_src_off; v->agg_dst = p.agg_dst_off;
+    v->node_counter = p.nc; v->edge_counter = p.ec; v->agg_src_ids = c->agg_src_ids; v->agg_dst_ids = c->agg_dst_ids;
+    v->capacity = c->capacity; v->max_rows = c->max_rows;
+    return LGN_OK;
+}
+
+int lgn_read_counters(lgn_ctx* c, void* stream, int32_t pipe, int32_t nc[16], int32_t ec[16])
+{
+    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH) return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(nc, c->pipe[pipe].nc, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ec, c->pipe[pipe].ec, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LGN_OK;
+}
+
+int lgn_tier_counts(lgn_ctx* c, void* stream, int64_t out[3], int32_t reset)
+{
+    if (!c || !out) return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, c->state->tier_rows, sizeof(h), cudaMemcpyDeviceToHost, s));
+    if (reset) CK(cudaMemsetAsync(c->state->tier_rows, 0, sizeof(h), s));
+    CK(cudaStreamSynchronize(s));
+    out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
+    return LGN_OK;
+}
+
+int lgn_status(lgn_ctx* c, void* stream)
+{
+    if (!c) return LGN_E_ARG;
+    int32_t st = 0;
+    CK(cudaMemcpyAsync(&st, &c->state->status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return st;
+}
+
+int lgn_hotness(lgn_ctx* c, uint32_t** node, uint32_t** topo)
+{
+    if (!c || !c->node_hotness) return LGN_E_STATE;
+    if (node) *node = c->node_hotness;
+    if (topo) *topo = c->topo_hotness;
+    return LGN_OK;
+}
+
+int32_t lgn_max_ids(lgn_ctx* c, void* stream)
+{
+    if (!c) return LGN_E_ARG;
+    int32_t v = 0;
+    if (cudaMemcpyAsync(&v, &c->state->max_ids, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return LGN_E_CUDA;
+    cudaStreamSynchronize((cudaStream_t)stream);
+    return v;
+}
+
+// ---------------------------------------------------------------- step arithmetic
+int lgn_coordinate(const int32_t* n_train, const int32_t* n_valid, const int32_t* n_test, int32_t parts, int32_t batch,
+                   int32_t epochs, lgn_steps* out)
+{
+    if (!n_train || !n_valid || !n_test || !out || parts <= 0 || parts > LGN_MAX_PARTS || batch <= 0) return LGN_E_ARG;
+    int32_t min_train = 1000000000, max_valid = 0, max_test = 0;      // CUDA_IPC_Service.cu:71-112
+    for (int i = 0; i < parts; i++) {
+        if (n_train[i] < min_train) min_train = n_train[i];
+        if (n_valid[i] > max_valid) max_valid = n_valid[i];
+        if (n_test[i] > max_test) max_test = n_test[i];
+    }
+    memset(out, 0, sizeof(*out));
+    out->train_step = (min_train - 1) / batch;
+    out->valid_step = (max_valid - 1) / 512 + 1;
+    out->test_step = (max_test - 1) / 512 + 1;
+    for (int i = 0; i < parts; i++) {
+        out->valid_batch[i] = (n_valid[i] - 1) / out->valid_step + 1;
+        out->test_batch[i] = (n_test[i] - 1) / out->test_step + 1;
+    }
+    out->max_step = (out->train_step + out->valid_step) * epochs + out->test_step;   // :136-138
+    return LGN_OK;
+}
+
+int32_t lgn_mode_of_step(const lgn_steps* s, int32_t epochs, int32_t g)
+{
+    if (g < (s->train_step + s->valid_step) * epochs)                                 // :246-259
+        return (g % (s->train_step + s->valid_step)) < s->train_step ? LGN_MODE_TRAIN : LGN_MODE_VALID;
+    return LGN_MODE_TEST;
+}
+
+int32_t lgn_local_batch_id(const lgn_steps* s, int32_t epochs, int32_t g)
+{
+    if (g < (s->train_step + s->valid_step) * epochs) {                               // :219-233
+        const int32_t e = g % (s->train_step + s->valid_step);
+        return e < s->train_step ? e : e - s->train_step;
+    }
+    return (g - (s->train_step + s->valid_step) * epochs) % s->test_step;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// context.h -- host-side per-GPU context (the reference's GPURunner + GPUMemoryPool,
+// Server.cu:167-364, GPUMemoryPool.cuh:7-208) and the kernel launch prototypes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace lgn {
+
+// read-only view of the three topology tiers handed to the sampler
+struct TopoView {
+    const int64_t* base_indptr;                 // full CSR (mapped host or device)
+    const int32_t* base_indices;
+    const int32_t* slot_of;                     // int32[N]: part*cap+row, -1 = miss, NULL = no cache
+    const int64_t* indptr_tab[LGN_MAX_PARTS];   // shard CSRs (local / peer)
+    const int32_t* indices_tab[LGN_MAX_PARTS];
+    long long cap;
+};
+
+// read-only view of the three feature tiers handed to the gather
+struct FeatView {
+    const float* base;                          // float32[N, D] (mapped host or device)
+    const int32_t* slot_of;                     // int32[N]: part*cap+row, -1 = miss, NULL = no cache
+    const float* shard_tab[LGN_MAX_PARTS];
+    long long cap;
+    int32_t my_part;
+    int32_t n_parts;
+};
+
+struct Pipe {
+    int32_t* ids;
+    float* features;
+    int32_t* labels;
+    int32_t* agg_src_off;
+    int32_t* agg_dst_off;
+    int32_t* nc;
+    int32_t* ec;
+};
+
+}  // namespace lgn
+
+struct lgn_ctx {
+    lgn_config cfg;
+    long long capacity;        // B*(1+f1+f1*f2+...)
+    long long max_rows;
+    long long max_slots;       // largest F_max*f over hops
+    lgn::Pipe pipe[LGN_PIPELINE_DEPTH];
+    int cur_pipe;
+    // scratch shared by the pipes
+    int32_t* slot_map;         // int32[N]
+    int32_t* agg_src_ids;      // raw ids, int32[capacity]
+    int32_t* agg_dst_ids;
+    int32_t* slot_dst;         // int32[max_slots]: uncompacted draw results of the current hop
+    unsigned long long* scan_status;   // decoupled look-back tile descriptors
+    int32_t* scan_ticket;      // int32[LGN_MAX_HOPS]
+    lgn::BatchState* state;    // device
+    int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
+    uint32_t* node_hotness;    // u32[N] or NULL
+    uint32_t* topo_hotness;
+    // bound storage
+    const int32_t* seed_ids[3];
+    const int32_t* seed_labels[3];
+    int32_t seed_count[3];
+    lgn::TopoView topo;
+    lgn::FeatView feat;
+    // second stream + events for the sampling/gather overlap of Server.cu:301-328
+    cudaStream_t gather_stream;
+    cudaEvent_t ev_hop[LGN_MAX_HOPS + 2];
+    cudaEvent_t ev_join;
+    int n_sm;
+};
+
+namespace lgn {
+// sampler.cu
+void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const int32_t* labels, int32_t src_off,
+                        int32_t count, uint32_t step);
+void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc);
+void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
+// gather.cu
+void launch_gather(lgn_ctx* c, cudaStream_t s, int segment);
+void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,
+                     float* dst, int n_sm, cudaStream_t s);
+}  // namespace lgn

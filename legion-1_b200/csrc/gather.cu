@@ -1,0 +1,166 @@
+// gather.cu -- feature extraction from the tiered cache for sm_100a.
+//
+// Replaces zero_copy_with_aggregated_cache (Kernels.cu:662-702), the cuckoo lookup of
+// FindFeat (GPUCache.cu:387-432, bght::bcht::find) and FeatFillUp (GPUCache.cu:200-205).
+//
+// One warp owns 32 consecutive output rows: lane l resolves row l's tier (direct-mapped
+// int32 slot table: one 4-byte read instead of up to three 128-byte cuckoo buckets), the
+// warp then streams the rows UNROLL at a time with 128-bit loads -- local HBM shard,
+// peer shard over NVLink (P2P load) or mapped host memory over PCIe (UVA zero-copy) are
+// all plain global addresses -- and writes them with 128-bit streaming stores.  The
+// reference runs one thread per float with a 64-bit divide and modulo per element.
+#include "context.h"
+
+namespace lgn {
+
+constexpr int GATHER_THREADS = 256;
+constexpr int GATHER_UNROLL = 4;
+
+// VEC: 16-byte vectors per lane per row (1 covers D <= 128, 2 covers D <= 256, ...)
+template <int VEC>
+__global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
+                                                              const int32_t* __restrict__ nc, int seg_slot,
+                                                              float* __restrict__ out, int dim, long long n_nodes,
+                                                              long long max_rows, BatchState* __restrict__ st)
+{
+    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];       // Kernels.cu:672-681
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * GATHER_THREADS) >> 5;
+    const int nvec = dim >> 2;
+    unsigned long long n_local = 0, n_peer = 0, n_host = 0;
+
+    for (int r0 = warp * 32; r0 < cnt; r0 += n_warps * 32) {
+        // lane l: tier + source pointer of row r0+l
+        const int r = r0 + lane;
+        const uint4* src = nullptr;
+        if (r < cnt && (long long)(off + r) < max_rows) {
+            const int32_t id = (int32_t)ld_nc_u32(ids + off + r);
+            if (id >= 0) {                                        // Kernels.cu:694
+                const long long nid = id < n_nodes ? id : id % n_nodes;
+                int32_t g = -1;
+                if (fv.slot_of) g = (int32_t)ld_nc_u32(fv.slot_of + nid);
+                if (g < 0) {                                      // miss -> host / base matrix (Kernels.cu:692-696)
+                    src = reinterpret_cast<const uint4*>(fv.base + nid * dim);
+                    n_host++;
+                } else {                                          // hit -> shard[g / cap][g % cap] (Kernels.cu:697-699)
+                    const int part = (int)(g / fv.cap);
+                    src = reinterpret_cast<const uint4*>(fv.shard_tab[part] + (g - part * fv.cap) * dim);
+                    if (part == fv.my_part) n_local++; else n_peer++;
+                }
+            }
+        } else if (r < cnt) {
+            st->status = LGN_E_CAPACITY;                          // reference: silent overflow (Server.cu:275)
+        }
+        const int rows = min(32, cnt - r0);
+        uint4* dst0 = reinterpret_cast<uint4*>(out + (long long)(off + r0) * dim);
+        for (int rr = 0; rr < rows; rr += GATHER_UNROLL) {
+            uint4 v[GATHER_UNROLL][VEC];
+            const uint4* sp[GATHER_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; u++) {
+                sp[u] = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, (unsigned long long)src, (rr + u) & 31));
+                if (rr + u >= rows) sp[u] = nullptr;
+            }
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; u++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++)
+                    if (sp[u] && lane + 32 * k < nvec) v[u][k] = ld_nc_v4(sp[u] + lane + 32 * k);
+#pragma unroll
+            for (int u = 0; u < GATHER_UNROLL; u++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++)
+                    if (sp[u] && lane + 32 * k < nvec) st_cs_v4(dst0 + (long long)(rr + u) * nvec + lane + 32 * k, v[u][k]);
+        }
+    }
+    // tier statistics for the hit-mix roofline: one atomic per warp per tier
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_local += __shfl_xor_sync(0xffffffffu, n_local, o);
+        n_peer += __shfl_xor_sync(0xffffffffu, n_peer, o);
+        n_host += __shfl_xor_sync(0xffffffffu, n_host, o);
+    }
+    if (lane == 0) {
+        if (n_local) atomicAdd(&st->tier_rows[0], n_local);
+        if (n_peer) atomicAdd(&st->tier_rows[1], n_peer);
+        if (n_host) atomicAdd(&st->tier_rows[2], n_host);
+    }
+}
+
+// scalar fallback: D not a multiple of 4 floats or a tier base not 16-byte aligned
+__global__ void __launch_bounds__(GATHER_THREADS) k_gather_scalar(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
+                                                                  const int32_t* __restrict__ nc, int seg_slot,
+                                                                  float* __restrict__ out, int dim, long long n_nodes,
+                                                                  long long max_rows, BatchState* __restrict__ st)
+{
+    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * GATHER_THREADS) >> 5;
+    for (int r = warp; r < cnt; r += n_warps) {
+        if ((long long)(off + r) >= max_rows) { if (lane == 0) st->status = LGN_E_CAPACITY; continue; }
+        const int32_t id = ids[off + r];
+        if (id < 0) continue;
+        const long long nid = id < n_nodes ? id : id % n_nodes;
+        int32_t g = fv.slot_of ? fv.slot_of[nid] : -1;
+        const float* src;
+        int tier;
+        if (g < 0) { src = fv.base + nid * dim; tier = 2; }
+        else { const int part = (int)(g / fv.cap); src = fv.shard_tab[part] + (g - part * fv.cap) * dim; tier = part == fv.my_part ? 0 : 1; }
+        float* dst = out + (long long)(off + r) * dim;
+        for (int k = lane; k < dim; k += 32) dst[k] = src[k];
+        if (lane == 0) atomicAdd(&st->tier_rows[tier], 1ull);
+    }
+}
+
+// shard fill: row r of shard j <- src[order[r*kg + j]] (FeatFillUp, GPUCache.cu:200-205)
+__global__ void __launch_bounds__(GATHER_THREADS) k_row_copy(const int32_t* __restrict__ order, long long n, long long cap,
+                                                             int kg, int j, const float* __restrict__ src, int dim,
+                                                             float* __restrict__ dst)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * GATHER_THREADS) >> 5;
+    const bool vec = (dim & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
+    for (long long r = warp; r < cap; r += n_warps) {
+        const long long rank = r * kg + j;
+        if (rank >= n) continue;
+        const long long id = order[rank];
+        if (vec) {
+            const uint4* s = reinterpret_cast<const uint4*>(src + id * dim);
+            uint4* d = reinterpret_cast<uint4*>(dst + r * dim);
+            for (int k = lane; k < (dim >> 2); k += 32) d[k] = ld_nc_v4(s + k);
+        } else {
+            for (int k = lane; k < dim; k += 32) dst[r * dim + k] = src[id * dim + k];
+        }
+    }
+}
+
+void launch_gather(lgn_ctx* c, cudaStream_t s, int segment)
+{
+    Pipe& p = c->pipe[c->cur_pipe];
+    const int dim = c->cfg.feat_dim;
+    const int seg_slot = 3 + 2 * segment;
+    bool vec = (dim & 3) == 0 && ((uintptr_t)c->feat.base & 15) == 0 && ((uintptr_t)p.features & 15) == 0;
+    for (int i = 0; i < c->feat.n_parts; i++) vec = vec && ((uintptr_t)c->feat.shard_tab[i] & 15) == 0;
+    const int blocks = c->n_sm * 8;   // 2048 threads / SM, grid-stride over 32-row chunks
+    FeatView fv = c->feat;
+    const int nvec = dim >> 2;
+    if (vec && nvec <= 32)
+        k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+    else if (vec && nvec <= 64)
+        k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+    else if (vec && nvec <= 128)
+        k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+    else
+        k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+}
+
+void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,
+                     float* dst, int n_sm, cudaStream_t s)
+{
+    k_row_copy<<<n_sm * 8, GATHER_THREADS, 0, s>>>(order, n, cap, kg, j, src, dim, dst);
+}
+
+}  // namespace lgn

@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's per-GPU pipeline objects over the C-ABI.
+
+`Runner` plays GPURunner + GPUMemoryPool (Server.cu:167-364): it owns one lgn_ctx and
+exposes the five operators (Operator.cu:10-123) under their reference roles.  The cache
+planning helpers mirror GPUCache::CandidateSelection / CostModel / FillUp
+(GPUCache.cu:578-826).  Every method is a thin call into liblegion_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DevArray, MappedHostArray, check, lib, _vp
+
+
+def _ptr(x):
+    if isinstance(x, MappedHostArray):
+        return C.c_void_p(x.ptr)
+    return _vp(x)
+
+
+class Runner:
+    def __init__(self, n_nodes, feat_dim, batch_size, fanout, device=0, part=0, rng_mode=_lib.RNG_PHILOX,
+                 rng_seed=0, max_feature_rows=0, enable_hotness=False):
+        cfg = _lib.Config()
+        cfg.device, cfg.part, cfg.n_nodes, cfg.feat_dim = device, part, n_nodes, feat_dim
+        cfg.batch_size, cfg.n_hops = batch_size, len(fanout)
+        for i, f in enumerate(fanout):
+            cfg.fanout[i] = f
+        cfg.rng_mode, cfg.rng_seed = rng_mode, rng_seed
+        cfg.max_feature_rows, cfg.enable_hotness = max_feature_rows, int(enable_hotness)
+        self.cfg = cfg
+        self.fanout = list(fanout)
+        self.handle = C.c_void_p()
+        check(lib().lgn_create(C.byref(cfg), C.byref(self.handle)), "lgn_create")
+        self.capacity = lib().lgn_capacity(self.handle)
+        self._keep = []          # bound arrays must outlive the context
+        self.pipe = 0
+
+    # ---- storage binding (GPUNodeStorage / GPUGraphStorage) -----------------------
+    def bind_seeds(self, mode, ids, labels):
+        self._keep += [ids, labels]
+        n = ids.shape[0]
+        check(lib().lgn_bind_seeds(self.handle, mode, _ptr(ids), _ptr(labels), C.c_int32(n)), "lgn_bind_seeds")
+
+    def bind_topology(self, indptr, indices):
+        self._keep += [indptr, indices]
+        check(lib().lgn_bind_topology(self.handle, _ptr(indptr), _ptr(indices)), "lgn_bind_topology")
+
+    def bind_topology_cache(self, indptr_shards, indices_shards, slot_of, cap):
+        self._keep += [indptr_shards, indices_shards, slot_of]
+        n = len(indptr_shards)
+        a = (C.c_void_p * max(n, 1))(*[_ptr(x).value for x in indptr_shards])
+        b = (C.c_void_p * max(n, 1))(*[_ptr(x).value for x in indices_shards])
+        check(lib().lgn_bind_topology_cache(self.handle, n, a, b, _ptr(slot_of), C.c_int64(cap)), "lgn_bind_topology_cache")
+
+    def bind_features(self, features):
+        self._keep.append(features)
+        check(lib().lgn_bind_features(self.handle, _ptr(features)), "lgn_bind_features")
+
+    def bind_feature_cache(self, shards, slot_of, cap):
+        self._keep += [shards, slot_of]
+        n = len(shards)
+        a = (C.c_void_p * max(n, 1))(*[_ptr(x).value for x in shards])
+        check(lib().lgn_bind_feature_cache(self.handle, n, a, _ptr(slot_of), C.c_int64(cap)), "lgn_bind_feature_cache")
+
+    # ---- operators ----------------------------------------------------------------
+    def batch_generate(self, mode, batch_size, counter, stream=None, pipe=None):
+        """Batch_Generator::run (Operator.cu:10-32)."""
+        if pipe is not None:
+            self.pipe = pipe
+        check(lib().lgn_batch_generate(self.handle, _vp(stream), self.pipe, mode, batch_size, counter), "lgn_batch_generate")
+
+    def batch_from_host(self, seeds, labels=None, step=0, stream=None, pipe=None):
+        if pipe is not None:
+            self.pipe = pipe
+        seeds = np.ascontiguousarray(seeds, np.int32) if isinstance(seeds, np.ndarray) else seeds
+        n = seeds.shape[0]
+        check(lib().lgn_batch_from_host(self.handle, _vp(stream), self.pipe, _ptr(seeds), _ptr(labels), C.c_int32(n),
+                                        C.c_uint32(step)), "lgn_batch_from_host")
+
+    def sample_hop(self, hop, is_presc=False, stream=None):
+        """Random_Sampler::run (Operator.cu:34-56)."""
+        check(lib().lgn_sample_hop(self.handle, _vp(stream), hop, int(is_presc)), "lgn_sample_hop")
+
+    def gather_segment(self, segment, stream=None):
+        """Feature_Extractor::run (Operator.cu:58-78)."""
+        check(lib().lgn_gather_segment(self.handle, _vp(stream), segment), "lgn_gather_segment")
+
+    def finish_batch(self, is_presc=False, stream=None):
+        """Cache_Planner::run + Cache_Updater::run (Operator.cu:80-123)."""
+        check(lib().lgn_finish_batch(self.handle, _vp(stream), int(is_presc)), "lgn_finish_batch")
+
+    def run_batch(self, with_features=True, is_presc=False, stream=None):
+        """GPURunner::RunOnce / RunPreSc minus the IPC handshake (Server.cu:284-328)."""
+        check(lib().lgn_run_batch(self.handle, _vp(stream), int(with_features), int(is_presc)), "lgn_run_batch")
+
+    # ---- results ------------------------------------------------------------------
+    def view(self, pipe=None):
+        v = _lib.BatchView()
+        check(lib().lgn_batch_buffers(self.handle, self.pipe if pipe is None else pipe, C.byref(v)), "lgn_batch_buffers")
+        return v
+
+    def read_counters(self, stream=None, pipe=None):
+        nc = np.zeros(16, np.int32)
+        ec = np.zeros(16, np.int32)
+        check(lib().lgn_read_counters(self.handle, _vp(stream), self.pipe if pipe is None else pipe, _vp(nc), _vp(ec)),
+              "lgn_read_counters")
+        return nc, ec
+
+    def fetch(self, with_features=True, stream=None):
+        """copy the whole batch to host numpy arrays (tests only)."""
+        nc, ec = self.read_counters(stream)
+        v = self.view()
+        n_hops = self.cfg.n_hops
+        total = int(nc[0])
+        n_e = int(ec[0])
+        cap = int(v.capacity)
+        get = lambda p, n, dt=np.int32: DevArray((cap,), dt, ptr=p, owner=False).numpy(n)
+        out = dict(nc=nc, ec=ec, sampled_ids=get(v.ids, total), agg_src_ids=get(v.agg_src_ids, n_e),
+                   agg_dst_ids=get(v.agg_dst_ids, n_e), agg_src_off=get(v.agg_src, n_e), agg_dst_off=get(v.agg_dst, n_e),
+                   labels=DevArray((self.cfg.batch_size,), np.int32, ptr=v.labels, owner=False).numpy(int(nc[4])))
+        if with_features and v.features:
+            rows = min(total, int(v.max_rows))
+            out["features"] = DevArray((int(v.max_rows), self.cfg.feat_dim), np.float32, ptr=v.features, owner=False).numpy(rows)
+        out["n_hops"] = n_hops
+        return out
+
+    def tier_counts(self, reset=False, stream=None):
+        out = (C.c_int64 * 3)()
+        check(lib().lgn_tier_counts(self.handle, _vp(stream), out, int(reset)), "lgn_tier_counts")
+        return list(out)
+
+    def status(self, stream=None):
+        return lib().lgn_status(self.handle, _vp(stream))
+
+    def hotness(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib().lgn_hotness(self.handle, C.byref(a), C.byref(b)), "lgn_hotness")
+        n = self.cfg.n_nodes
+        return DevArray((n,), np.uint32, ptr=a.value, owner=False), DevArray((n,), np.uint32, ptr=b.value, owner=False)
+
+    def max_ids(self, stream=None):
+        return lib().lgn_max_ids(self.handle, _vp(stream))
+
+    def close(self):
+        if self.handle:
+            lib().lgn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- planner (GPUCache::CandidateSelection / CostModel / FillUp) ------------------------
+def hot_order(counts, want_sorted=False, stream=None):
+    n = counts.shape[0]
+    order = DevArray((n,), np.int32)
+    sorted_counts = DevArray((n,), np.uint32) if want_sorted else None
+    check(lib().lgn_hot_order(_ptr(counts), C.c_int64(n), _ptr(order), _ptr(sorted_counts), _vp(stream)), "lgn_hot_order")
+    return (order, sorted_counts) if want_sorted else order
+
+
+def place(order, cap, kg, stream=None):
+    n = order.shape[0]
+    slot_of = DevArray((n,), np.int32)
+    check(lib().lgn_place(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), _ptr(slot_of), _vp(stream)), "lgn_place")
+    return slot_of
+
+
+def fill_feature_shard(order, cap, kg, j, features, dim, stream=None, out=None):
+    n = order.shape[0]
+    shard = out if out is not None else DevArray.zeros((cap, dim), np.float32)
+    check(lib().lgn_fill_feature_shard(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),
+                                       _ptr(features), C.c_int32(dim), _ptr(shard), _vp(stream)), "lgn_fill_feature_shard")
+    return shard
+
+
+def fill_topo_shard(order, cap, kg, j, indptr, indices, stream=None):
+    n = order.shape[0]
+    ip = DevArray((cap + 1,), np.int64)
+    cnt = C.c_int64()
+    args = (_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int32(j), _ptr(indptr), _ptr(indices), _ptr(ip))
+    check(lib().lgn_fill_topo_shard(*args, None, C.byref(cnt), _vp(stream)), "lgn_fill_topo_shard(size)")
+    ix = DevArray((max(cnt.value, 1),), np.int32)
+    check(lib().lgn_fill_topo_shard(*args, _ptr(ix), C.byref(cnt), _vp(stream)), "lgn_fill_topo_shard(fill)")
+    return ip, ix, cnt.value
+
+
+def cost_model(af_sorted, at_sorted, qt, indptr, dim, cache_memory, kg, topo_trans, max_ids, train_step):
+    n = qt.shape[0]
+    mi = (C.c_int32 * len(max_ids))(*max_ids)
+    ncap, ecap = C.c_int32(), C.c_int32()
+    check(lib().lgn_cost_model(_ptr(af_sorted), _ptr(at_sorted), _ptr(qt), _ptr(indptr), C.c_int64(n), C.c_int32(dim),
+                               C.c_int64(cache_memory), C.c_int32(kg), C.c_uint64(topo_trans), mi, C.c_int32(train_step),
+                               C.byref(ncap), C.byref(ecap)), "lgn_cost_model")
+    return ncap.value, ecap.value
+
+
+def coordinate(n_train, n_valid, n_test, batch, epochs):
+    s = _lib.Steps()
+    P = len(n_train)
+    arr = lambda v: (C.c_int32 * P)(*v)
+    check(lib().lgn_coordinate(arr(n_train), arr(n_valid), arr(n_test), C.c_int32(P), C.c_int32(batch), C.c_int32(epochs),
+                               C.byref(s)), "lgn_coordinate")
+    return s

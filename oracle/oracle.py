@@ -1,0 +1,209 @@
+"""ctypes/numpy front end of the CPU oracle (oracle/legion_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(legion-1_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblegion_oracle.so")
+
+RNG_MINSTD, RNG_PHILOX = 0, 1
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("legion_oracle.c", "legion_oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.lgo_minstd_pow.restype = C.c_uint32
+        _lib.lgo_minstd_pow.argtypes = [C.c_uint64]
+        _lib.lgo_minstd_pick.restype = C.c_int32
+        _lib.lgo_minstd_pick.argtypes = [C.c_uint64, C.c_int32]
+        _lib.lgo_philox_pick.restype = C.c_int32
+        _lib.lgo_philox_pick.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32]
+        _lib.lgo_batch_generate.restype = C.c_int32
+        _lib.lgo_fill_topo_shard.restype = C.c_int64
+        _lib.lgo_mode_of_step.restype = C.c_int32
+        _lib.lgo_local_batch_id.restype = C.c_int32
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p),
+        ("n_hops", C.c_int32), ("fanout", C.c_void_p), ("rng_mode", C.c_int32),
+        ("rng_seed", C.c_uint64), ("step", C.c_uint32),
+        ("capacity", C.c_int64), ("n_seeds", C.c_int32),
+        ("sampled_ids", C.c_void_p), ("agg_src_ids", C.c_void_p), ("agg_dst_ids", C.c_void_p),
+        ("agg_src_off", C.c_void_p), ("agg_dst_off", C.c_void_p),
+        ("nc", C.c_void_p), ("ec", C.c_void_p), ("position_map", C.c_void_p),
+        ("topo_hotness", C.c_void_p), ("node_hotness", C.c_void_p), ("n_threads", C.c_int32),
+    ]
+
+
+class Steps(C.Structure):
+    _fields_ = [("train_step", C.c_int32), ("valid_step", C.c_int32), ("test_step", C.c_int32),
+                ("max_step", C.c_int32), ("valid_batch", C.c_int32 * 8), ("test_batch", C.c_int32 * 8)]
+
+
+def minstd_pick(idx, deg):
+    return lib().lgo_minstd_pick(int(idx), int(deg))
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().lgo_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def philox_pick(idx, hop, step, seed, deg):
+    return lib().lgo_philox_pick(int(idx), int(hop), int(step), int(seed), int(deg))
+
+
+def capacity_for(batch, fanout):
+    """Server.cu:184-196: B*(1 + f1 + f1*f2 + ...)."""
+    tot, cur = batch, batch
+    for f in fanout:
+        cur *= f
+        tot += cur
+    return tot
+
+
+def batch_generate(all_ids, all_labels, batch_size, counter):
+    ids = np.full(batch_size, -1, np.int32)
+    labels = np.full(batch_size, -1, np.int32)
+    n = lib().lgo_batch_generate(_p(all_ids), _p(all_labels), C.c_int32(len(all_ids)),
+                                 C.c_int32(batch_size), C.c_int32(counter), _p(ids), _p(labels))
+    return ids[:n].copy(), labels[:n].copy()
+
+
+class Sampler:
+    """k-hop sampler + dedup + relabel (Kernels.cu:342-463)."""
+
+    def __init__(self, indptr, indices, fanout, rng_mode=RNG_PHILOX, rng_seed=0, capacity=None, n_threads=1):
+        self.indptr = np.ascontiguousarray(indptr, np.int64)
+        self.indices = np.ascontiguousarray(indices, np.int32)
+        self.n = len(self.indptr) - 1
+        self.fanout = np.asarray(fanout, np.int32)
+        self.rng_mode, self.rng_seed, self.n_threads = rng_mode, rng_seed, n_threads
+        self.pos = np.full(self.n, -1, np.int32)
+        self.capacity = capacity
+        self.topo_hotness = None
+        self.node_hotness = None
+
+    def enable_hotness(self):
+        self.topo_hotness = np.zeros(self.n, np.uint32)
+        self.node_hotness = np.zeros(self.n, np.uint32)
+
+    def sample(self, seeds, step=0):
+        seeds = np.asarray(seeds, np.int32)
+        B = len(seeds)
+        cap = self.capacity or capacity_for(max(B, 1), self.fanout.tolist())
+        out = {k: np.full(cap, -1, np.int32) for k in
+               ("sampled_ids", "agg_src_ids", "agg_dst_ids", "agg_src_off", "agg_dst_off")}
+        out["sampled_ids"][:B] = seeds
+        nc = np.zeros(16, np.int32)
+        ec = np.zeros(16, np.int32)
+        a = SampleArgs(self.n, _p(self.indptr), _p(self.indices), len(self.fanout), _p(self.fanout),
+                       self.rng_mode, self.rng_seed, step, cap, B,
+                       _p(out["sampled_ids"]), _p(out["agg_src_ids"]), _p(out["agg_dst_ids"]),
+                       _p(out["agg_src_off"]), _p(out["agg_dst_off"]), _p(nc), _p(ec), _p(self.pos),
+                       _p(self.topo_hotness), _p(self.node_hotness), self.n_threads)
+        rc = lib().lgo_sample_batch(C.byref(a))
+        if rc != 0:
+            raise RuntimeError(f"lgo_sample_batch failed rc={rc}")
+        out["nc"], out["ec"] = nc, ec
+        return out
+
+
+def hot_order(counts):
+    counts = np.ascontiguousarray(counts, np.uint32)
+    order = np.empty(len(counts), np.int32)
+    lib().lgo_hot_order(_p(counts), C.c_int64(len(counts)), _p(order))
+    return order
+
+
+def place(order, cap, kg):
+    slot = np.empty(len(order), np.int32)
+    lib().lgo_place(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), _p(slot))
+    return slot
+
+
+def fill_feature_shard(order, cap, kg, j, features):
+    features = np.ascontiguousarray(features, np.float32)
+    shard = np.zeros((cap, features.shape[1]), np.float32)
+    lib().lgo_fill_feature_shard(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),
+                                 _p(features), C.c_int32(features.shape[1]), _p(shard))
+    return shard
+
+
+def fill_topo_shard(order, cap, kg, j, indptr, indices):
+    ip = np.zeros(cap + 1, np.int64)
+    n = lib().lgo_fill_topo_shard(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),
+                                  _p(indptr), _p(indices), _p(ip), None)
+    ix = np.zeros(max(n, 1), np.int32)
+    lib().lgo_fill_topo_shard(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),
+                              _p(indptr), _p(indices), _p(ip), _p(ix))
+    return ip, ix[:n]
+
+
+def cost_model(af, at, qt, indptr, dim, cache_memory, kg, topo_trans, max_ids, train_step):
+    af = np.ascontiguousarray(af, np.uint64)
+    at = np.ascontiguousarray(at, np.uint64)
+    qt = np.ascontiguousarray(qt, np.int32)
+    mi = np.ascontiguousarray(max_ids, np.int32)
+    ncap, ecap, best = C.c_int32(), C.c_int32(), C.c_int32()
+    lib().lgo_cost_model(_p(af), _p(at), _p(qt), _p(indptr), C.c_int64(len(qt)), C.c_int32(dim),
+                         C.c_int64(cache_memory), C.c_int32(kg), C.c_uint64(topo_trans), _p(mi),
+                         C.c_int32(train_step), C.byref(ncap), C.byref(ecap), C.byref(best))
+    return ncap.value, ecap.value, best.value
+
+
+def gather(sampled_ids, off, cnt, slot_of, cap, shards, host_features, out, n_threads=1, tiers=False):
+    host_features = np.ascontiguousarray(host_features, np.float32)
+    n, dim = host_features.shape
+    ns = len(shards) if shards else 0
+    ptrs = (C.c_void_p * max(ns, 1))(*[s.ctypes.data for s in (shards or [])])
+    tr = np.zeros(ns + 1, np.int64) if tiers else None
+    lib().lgo_gather(_p(sampled_ids), C.c_int32(off), C.c_int32(cnt), _p(slot_of), C.c_int64(max(cap, 1)), ptrs,
+                     _p(host_features), C.c_int64(n), C.c_int32(dim), _p(out), _p(tr), C.c_int32(ns),
+                     C.c_int32(n_threads))
+    return tr
+
+
+def coordinate(n_train, n_valid, n_test, batch, epochs):
+    s = Steps()
+    P = len(n_train)
+    arr = lambda v: (C.c_int32 * P)(*v)
+    lib().lgo_coordinate(arr(n_train), arr(n_valid), arr(n_test), C.c_int32(P), C.c_int32(batch), C.c_int32(epochs),
+                         C.byref(s))
+    return s
+
+
+def mode_of_step(s, epochs, g):
+    return lib().lgo_mode_of_step(C.byref(s), C.c_int32(epochs), C.c_int32(g))
+
+
+def local_batch_id(s, epochs, g):
+    return lib().lgo_local_batch_id(C.byref(s), C.c_int32(epochs), C.c_int32(g))

@@ -1,0 +1,312 @@
+"""Parity tests proper: the CUDA hot path (through the C-ABI) against the CPU oracle on the
+same seeded inputs.  Integer / index / byte work throughout => every comparison is bit-exact.
+Edge cases follow the reference's own branches: padded (-1) seeds (Kernels.cu:81-83,385),
+clamped last batch (Kernels.cu:224), zero-degree nodes (Kernels.cu:399), duplicates in the
+frontier (Kernels.cu:371-373), cache hit / miss tiers (Kernels.cu:692-699)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ("nc", "ec", "sampled_ids", "agg_src_ids", "agg_dst_ids", "agg_src_off", "agg_dst_off")
+
+
+def _oracle_batch(O, smp, seeds, step):
+    out = smp.sample(seeds, step=step)
+    total, n_e = int(out["nc"][0]), int(out["ec"][0])
+    res = {k: out[k] for k in ("nc", "ec")}
+    res["sampled_ids"] = out["sampled_ids"][:total]
+    for k in ("agg_src_ids", "agg_dst_ids", "agg_src_off", "agg_dst_off"):
+        res[k] = out[k][:n_e]
+    return res
+
+
+def _assert_same(got, want, keys=INT_KEYS, ctx=""):
+    for k in keys:
+        assert got[k].shape == want[k].shape, f"{ctx}{k}: shape {got[k].shape} vs {want[k].shape}"
+        assert np.array_equal(got[k], want[k]), f"{ctx}{k} differs (first at {np.flatnonzero(got[k] != want[k])[:5]})"
+
+
+def _make_runner(L, d, batch, fanout, rng_mode, seed=7, feat=True, **kw):
+    r = L.Runner(d.n_nodes, d.dim if feat else 0, batch, fanout, rng_mode=rng_mode, rng_seed=seed, **kw)
+    ip, ix = L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices)
+    r.bind_topology(ip, ix)
+    if feat:
+        r.bind_features(L.DevArray.from_numpy(d.features))
+    return r
+
+
+@pytest.mark.parametrize("rng", ["minstd", "philox"])
+@pytest.mark.parametrize("fanout", [[25, 10], [15, 10, 5], [3], [40, 2]])
+def test_sampling_bit_exact(c1, rng, fanout):
+    import legion_b200 as L
+    from oracle import oracle as O
+    mode = L.RNG_MINSTD if rng == "minstd" else L.RNG_PHILOX
+    B = 1024
+    r = _make_runner(L, c1, B, fanout, mode, feat=False)
+    smp = O.Sampler(c1.indptr, c1.indices, fanout, rng_mode=mode, rng_seed=7)
+    train = c1.train_ids
+    for step in range(3):
+        seeds = train[step * B:(step + 1) * B]
+        r.batch_from_host(seeds, None, step=step, pipe=step % 2)
+        for h in range(len(fanout)):
+            r.sample_hop(h)
+        r.finish_batch()
+        got = r.fetch(with_features=False)
+        want = _oracle_batch(O, smp, seeds, step)
+        _assert_same(got, want, ctx=f"{rng} {fanout} step {step}: ")
+        assert r.status() == 0
+    r.close()
+
+
+def test_sampling_edge_cases(small):
+    """ragged / empty / padded / duplicate seeds, zero-degree nodes."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = small
+    # make some isolated nodes and a hub so deg==0, deg<f, deg>f all occur
+    indptr, indices = d.indptr.copy(), d.indices.copy()
+    fanout = [5, 4]
+    for mode in (L.RNG_MINSTD, L.RNG_PHILOX):
+        r = L.Runner(d.n_nodes, 0, 64, fanout, rng_mode=mode, rng_seed=123)
+        r.bind_topology(L.DevArray.from_numpy(indptr), L.DevArray.from_numpy(indices))
+        smp = O.Sampler(indptr, indices, fanout, rng_mode=mode, rng_seed=123)
+        cases = [
+            np.array([], np.int32),
+            np.array([5], np.int32),
+            np.array([7, -1, 9, -1], np.int32),                        # padding ids (Kernels.cu:81-83)
+            np.array([11, 11, 12, 11, 40, 12], np.int32),              # duplicate seeds (lp_sage layout)
+            np.arange(0, 64, dtype=np.int32),
+            np.full(10, -1, np.int32),
+        ]
+        for step, seeds in enumerate(cases):
+            r.batch_from_host(seeds, None, step=step)
+            for h in range(len(fanout)):
+                r.sample_hop(h)
+            r.finish_batch()
+            got = r.fetch(with_features=False)
+            want = _oracle_batch(O, smp, seeds, step)
+            _assert_same(got, want, ctx=f"mode {mode} case {step}: ")
+        r.close()
+
+
+def test_full_neighbourhood_when_fanout_covers_degree(small):
+    """north star: exact full-neighbourhood results when fanout >= degree (philox mode)."""
+    import legion_b200 as L
+    d = small
+    deg = np.diff(d.indptr)
+    f = int(deg.max())
+    assert f <= 256
+    seeds = np.arange(0, 200, dtype=np.int32)
+    r = L.Runner(d.n_nodes, 0, 256, [f], rng_mode=L.RNG_PHILOX, rng_seed=1)
+    r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+    r.batch_from_host(seeds, None, step=0)
+    r.sample_hop(0)
+    r.finish_batch()
+    got = r.fetch(with_features=False)
+    src_of_edge, dst_of_edge = got["agg_dst_ids"], got["agg_src_ids"]
+    pos = 0
+    for s in seeds:
+        nb = d.indices[d.indptr[s]:d.indptr[s + 1]]
+        assert np.array_equal(dst_of_edge[pos:pos + len(nb)], nb)
+        assert np.all(src_of_edge[pos:pos + len(nb)] == s)
+        pos += len(nb)
+    assert pos == len(dst_of_edge)
+    r.close()
+
+
+def test_batch_generate_matches_reference_indexing(small):
+    """op 0 incl. the clamped last batch (Kernels.cu:224-227) and labels."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = small
+    ids = d.test_ids.astype(np.int32)
+    labels = d.labels[ids]
+    r = L.Runner(d.n_nodes, 0, 16, [2])
+    r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+    r.bind_seeds(L.MODE_TEST, L.DevArray.from_numpy(ids), L.DevArray.from_numpy(labels))
+    B = 16
+    steps = (len(ids) - 1) // B + 1
+    for counter in range(steps):
+        r.batch_generate(L.MODE_TEST, B, counter)
+        r.sample_hop(0)
+        r.finish_batch()
+        got = r.fetch(with_features=False)
+        w_ids, w_lab = O.batch_generate(ids, labels, B, counter)
+        assert np.array_equal(got["sampled_ids"][:len(w_ids)], w_ids)
+        assert np.array_equal(got["labels"], w_lab)
+        assert got["nc"][4] == len(w_ids)
+    r.close()
+
+
+@pytest.mark.parametrize("dim", [100, 128, 256, 7])
+@pytest.mark.parametrize("kg,frac,host", [(1, 1.0, False), (1, 0.3, True), (4, 0.5, True), (8, 1.0, False), (0, 0.0, True)])
+def test_gather_bit_exact(dim, kg, frac, host):
+    """all three tiers: local shard, 'peer' shards (separate allocations addressed through the
+    shard table, emulated on one GPU), base matrix in mapped host memory (UVA zero-copy)."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = L.synth.make_dataset(20_000, 10.0, dim, n_class=5)
+    fanout = [10, 5]
+    B = 512
+    r = L.Runner(d.n_nodes, dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=3, part=0)
+    r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+    base = L.MappedHostArray.from_numpy(d.features) if host else L.DevArray.from_numpy(d.features)
+    r.bind_features(base)
+    slot_h, shards_h, cap = None, [], 1
+    if kg > 0:
+        rng = np.random.default_rng(5)
+        counts = rng.integers(0, 50, d.n_nodes).astype(np.uint32)
+        order_h = O.hot_order(counts)
+        cap = int(np.ceil(d.n_nodes * frac / kg))
+        slot_h = O.place(order_h, cap, kg)
+        shards_h = [O.fill_feature_shard(order_h, cap, kg, j, d.features) for j in range(kg)]
+        order_d = L.hot_order(L.DevArray.from_numpy(counts))
+        assert np.array_equal(order_d.numpy(), order_h)
+        slot_d = L.place(order_d, cap, kg)
+        assert np.array_equal(slot_d.numpy(), slot_h)
+        shards_d = [L.fill_feature_shard(order_d, cap, kg, j, base, dim) for j in range(kg)]
+        for j in range(kg):   # cache contents bit-exact
+            assert np.array_equal(shards_d[j].numpy().view(np.uint32), shards_h[j].view(np.uint32))
+        r.bind_feature_cache(shards_d, slot_d, cap)
+    smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=3)
+    for step in range(2):
+        seeds = d.train_ids[step * B:(step + 1) * B]
+        r.batch_from_host(seeds, d.labels[seeds], step=step)
+        r.run_batch(with_features=True)
+        got = r.fetch()
+        want = _oracle_batch(O, smp, seeds, step)
+        _assert_same(got, want)
+        total = int(want["nc"][0])
+        ref = np.zeros((total, dim), np.float32)
+        tiers = O.gather(want["sampled_ids"], 0, total, slot_h, cap, shards_h, d.features, ref, tiers=True)
+        assert np.array_equal(got["features"].view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(got["labels"], d.labels[seeds])
+        tc = r.tier_counts(reset=True)
+        assert tc[0] + tc[1] + tc[2] == total
+        if kg > 0:
+            assert tc[0] == tiers[0] and tc[1] == tiers[1:kg].sum() and tc[2] == tiers[kg]
+    r.close()
+
+
+def test_presampling_hotness_and_planner(c1):
+    """presampling epoch: node / topology hotness, max ids, hot order, shards, cost model."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = c1
+    fanout, B, steps = [25, 10], 1024, 5
+    for mode in (L.RNG_MINSTD, L.RNG_PHILOX):
+        r = L.Runner(d.n_nodes, d.dim, B, fanout, rng_mode=mode, rng_seed=11, enable_hotness=True)
+        ipd, ixd = L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices)
+        r.bind_topology(ipd, ixd)
+        ids = d.train_ids
+        r.bind_seeds(L.MODE_TRAIN, L.DevArray.from_numpy(ids), L.DevArray.from_numpy(d.labels[ids]))
+        smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=mode, rng_seed=11)
+        smp.enable_hotness()
+        max_ids = 0
+        for step in range(steps):
+            r.batch_generate(L.MODE_TRAIN, B, step, pipe=step % 2)
+            r.run_batch(with_features=False, is_presc=True)
+            w = smp.sample(ids[step * B:(step + 1) * B], step=step)
+            max_ids = max(max_ids, int(w["nc"][0]))
+        nh, th = r.hotness()
+        assert np.array_equal(nh.numpy(), smp.node_hotness)
+        assert np.array_equal(th.numpy(), smp.topo_hotness)
+        assert r.max_ids() == max_ids
+        # candidate selection
+        qf, af = L.hot_order(nh, want_sorted=True)
+        qt, at = L.hot_order(th, want_sorted=True)
+        qf_h, qt_h = O.hot_order(smp.node_hotness), O.hot_order(smp.topo_hotness)
+        assert np.array_equal(qf.numpy(), qf_h) and np.array_equal(qt.numpy(), qt_h)
+        assert np.array_equal(af.numpy(), smp.node_hotness[qf_h])
+        # cost model (restricted cache so both tiers compete)
+        cache_mem = 20_000_000
+        for kg in (1, 2):
+            got = L.cost_model(af, at, qt, ipd, d.dim, cache_mem, kg, 123456, [max_ids] * kg, steps)
+            want = O.cost_model(smp.node_hotness[qf_h], smp.topo_hotness[qt_h], qt_h, d.indptr, d.dim, cache_mem, kg,
+                                123456, [max_ids] * kg, steps)
+            assert got == want[:2], (got, want)
+        # topology shards
+        kg, cap = 4, 9000
+        for j in range(kg):
+            ip_d, ix_d, n = L.fill_topo_shard(qt, cap, kg, j, ipd, ixd)
+            ip_h, ix_h = O.fill_topo_shard(qt_h, cap, kg, j, d.indptr, d.indices)
+            assert n == len(ix_h)
+            assert np.array_equal(ip_d.numpy(), ip_h)
+            assert np.array_equal(ix_d.numpy(n), ix_h)
+        r.close()
+
+
+def test_topology_cache_tiers(c1):
+    """train-time sampler over a sharded topology cache: hits read shard CSRs, misses the
+    base CSR in mapped host memory -- same samples as the flat CSR (Kernels.cu:389-410)."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = c1
+    fanout, B = [25, 10], 1024
+    rng = np.random.default_rng(9)
+    counts = rng.integers(0, 100, d.n_nodes).astype(np.uint32)
+    ipd, ixd = L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices)
+    qt = L.hot_order(L.DevArray.from_numpy(counts))
+    kg, cap = 4, 15_000    # 60 % of the nodes cached over 4 shards
+    slot = L.place(qt, cap, kg)
+    shards = [L.fill_topo_shard(qt, cap, kg, j, ipd, ixd) for j in range(kg)]
+    for mode in (L.RNG_MINSTD, L.RNG_PHILOX):
+        r = L.Runner(d.n_nodes, 0, B, fanout, rng_mode=mode, rng_seed=2)
+        r.bind_topology(L.MappedHostArray.from_numpy(d.indptr), L.MappedHostArray.from_numpy(d.indices))
+        r.bind_topology_cache([s[0] for s in shards], [s[1] for s in shards], slot, cap)
+        smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=mode, rng_seed=2)
+        for step in range(2):
+            seeds = d.train_ids[step * B:(step + 1) * B]
+            r.batch_from_host(seeds, None, step=step)
+            r.run_batch(with_features=False)
+            _assert_same(r.fetch(with_features=False), _oracle_batch(O, smp, seeds, step))
+        r.close()
+
+
+def test_run_batch_overlap_equals_stepwise_and_pipes(c1):
+    """two-stream RunOnce DAG == operator-by-operator execution; alternating pipe slots keep
+    the previous batch intact (double buffering, Server.cu:325-327)."""
+    import legion_b200 as L
+    d = c1
+    fanout, B = [25, 10], 1024
+    r = _make_runner(L, d, B, fanout, L.RNG_PHILOX)
+    seeds0, seeds1 = d.train_ids[:B], d.train_ids[B:2 * B]
+    r.batch_from_host(seeds0, d.labels[seeds0], step=0, pipe=0)
+    r.run_batch(with_features=True)
+    a0 = r.fetch()
+    r.batch_from_host(seeds1, d.labels[seeds1], step=1, pipe=1)
+    for seg in range(len(fanout) + 1):
+        if seg > 0:
+            r.sample_hop(seg - 1)
+        r.gather_segment(seg)
+    r.finish_batch()
+    b1 = r.fetch()
+    r.pipe = 0
+    a0_again = r.fetch()
+    for k in INT_KEYS + ("features", "labels"):
+        assert np.array_equal(a0[k], a0_again[k]), k
+    # and the same batch through both paths
+    r.batch_from_host(seeds1, d.labels[seeds1], step=1, pipe=0)
+    r.run_batch(with_features=True)
+    b1_dag = r.fetch()
+    for k in INT_KEYS + ("features", "labels"):
+        assert np.array_equal(b1[k], b1_dag[k]), k
+    r.close()
+
+
+def test_capacity_overflow_is_reported(small):
+    """reference: silent overflow of the 1.2x feature buffer (Server.cu:275); here: status code."""
+    import legion_b200 as L
+    d = small
+    r = L.Runner(d.n_nodes, d.dim, 256, [10, 5], max_feature_rows=300)
+    r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+    r.bind_features(L.DevArray.from_numpy(d.features))
+    r.batch_from_host(d.train_ids[:256], None, step=0)
+    r.run_batch(with_features=True)
+    nc, _ = r.read_counters()
+    assert nc[0] > 300
+    assert r.status() == L._lib.E_CAPACITY
+    with pytest.raises(L.LegionError):
+        r.batch_from_host(np.zeros(1000, np.int32), None)
+    r.close()
