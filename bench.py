@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py -- Legion mini-batch hot path on N B200s (one process per GPU).
+
+A "step" is one mini-batch of the pipeline on every rank: batch generation, k-hop neighbour
+sampling, dedup/relabel and feature extraction from the NVLink-clique-partitioned cache.
+Headline metric (BASELINE.json): sampled edges/s (whole job), with feature-extract GB/s and a
+GraphSAGE data-loading epoch estimate in `extra`.  Workload at every N: BASELINE.json configs[1],
+the ogbn-products-shaped synthetic graph (2,449,029 nodes, ~61.9 M edges, 100-d features),
+batch 8000 per GPU, fanout [25,10] -- weak scaling: each rank draws its own `tid % N` seed
+partition, the feature cache is sharded over the N GPUs and peer shards are read with P2P loads.
+
+  python bench.py --gpus 1 --steps 50 --warmup 10
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference        # CPU arm: the oracle port of the reference path
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sampled edges/s"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--rng", default="philox", choices=["philox", "minstd"])
+    ap.add_argument("--cache-frac", type=float, default=1.0, help="fraction of rows cached in HBM (rest: host UVA tier)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nodes", type=int, default=0, help="override node count (debug)")
+    ap.add_argument("--probe", action="store_true", help="debug: time sampling-only and gather-only loops")
+    ap.add_argument("--lanes", type=int, default=4, help="mini-batches in flight per GPU (batch slots)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.proc, self.lines = dev, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    import legion_b200 as L
+    cfg = dict(L.synth.CONFIGS[args.config])
+    if args.nodes:
+        cfg["n_nodes"] = args.nodes
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, all host threads, bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_leg(ds, cfg, seconds, steps_cap, rng_mode, seed, first_step=0):
+    """returns (edges/s, GB/s, n_batches, cores).  Same semantics as the GPU path; gathers rows by
+    memcpy from the host feature matrix (the reference has no CPU path of its own: SURVEY 8d)."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    B, fanout = cfg["batch"], cfg["fanout"]
+    smp = O.Sampler(ds.indptr, ds.indices, fanout, rng_mode=rng_mode, rng_seed=seed, n_threads=cores)
+    cap = O.capacity_for(B, fanout)
+    out = np.empty((cap, ds.dim), np.float32)
+    train = ds.train_ids
+    epoch_steps = max(1, (len(train) - 1) // B)
+    edges = rows = done = 0
+    t0 = time.perf_counter()
+    for it in range(steps_cap):          # cycles over the epoch's batches until the time budget is spent
+        step = (first_step + it) % epoch_steps
+        seeds = train[step * B:(step + 1) * B]
+        o = smp.sample(seeds, step=step)
+        total = int(o["nc"][0])
+        O.gather(o["sampled_ids"], 0, total, None, 1, [], ds.features, out, n_threads=cores)
+        edges += int(o["ec"][0]); rows += total; done += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return edges / dt, rows * ds.dim * 4 / dt / 1e9, done, cores, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own semantics on the host cores (oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import legion_b200 as L
+    from oracle import oracle as O
+    cfg = workload(args)
+    ds = L.synth.make_dataset(cfg["n_nodes"], cfg["avg_deg"], cfg["dim"], n_class=cfg["n_class"])
+    mode = O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD
+    per_step_budget = 8.0
+    # warm-up + K steps, each step = a bounded sample (1 batch) of the workload
+    for _ in range(min(args.warmup, 2)):
+        cpu_leg(ds, cfg, per_step_budget, 1, mode, 42)
+    t_edges, t_time, gbs = 0.0, 0.0, []
+    k = max(1, min(args.steps, 10))
+    for i in range(k):
+        eps, gb, n, cores, dt = cpu_leg(ds, cfg, per_step_budget, 1, mode, 42, first_step=i)
+        t_edges += eps * dt; t_time += dt; gbs.append(gb)
+    value = t_edges / t_time
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * t_time / k, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
+            "config": {"workload": f"{args.config} ogbn-products-shaped synthetic, batch {cfg['batch']}, fanout {cfg['fanout']}, "
+                                   f"{cfg['dim']}-d, CPU sampling+gather (oracle port of the reference path)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{k} steps x 1 batch of {cfg['batch']} seeds"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "extra": {"feature_extract_GBps": float(np.mean(gbs))}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import legion_b200 as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload(args)
+    N, D, B, fanout = cfg["n_nodes"], cfg["dim"], cfg["batch"], cfg["fanout"]
+    rng_mode = L.RNG_PHILOX if args.rng == "philox" else L.RNG_MINSTD
+
+    # ---- dataset, resident in HBM before the timed region --------------------------------
+    dmin = L.synth.calibrate_dmin(cfg["avg_deg"], N)
+    ds = L.synth.make_dataset(N, cfg["avg_deg"], D, n_class=cfg["n_class"], backend="torch", device=dev, dmin_fp=dmin)
+    torch.cuda.synchronize()
+    my_train = ds.train_ids[(ds.train_ids % world) == rank].contiguous()          # GPUGraphStore.cu:338
+    my_labels = ds.labels[my_train.long()].contiguous()
+    n_train = torch.tensor([my_train.numel()], device=dev)
+    if world > 1:
+        dist.all_reduce(n_train, op=dist.ReduceOp.MIN)
+    train_steps = (int(n_train.item()) - 1) // B                                    # CUDA_IPC_Service.cu:88
+
+    r = L.Runner(N, D, B, fanout, device=local, part=rank, rng_mode=rng_mode, rng_seed=42, enable_hotness=True, n_lanes=args.lanes)
+    r.bind_topology(ds.indptr, ds.indices)            # topology replicated in HBM (7 % of one B200 even for papers100M)
+    r.bind_seeds(L.MODE_TRAIN, my_train, my_labels)
+    # one sampling stream per pipeline slot (two independent lanes, PIPELINE_DEPTH 2) + a consumer-side stream
+    NL = args.lanes
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
+    lp = [x.cuda_stream for x in lanes]
+    stream, sp = lanes[0], lp[0]
+    stream2 = torch.cuda.Stream(device=dev)       # consumer-side stream of the e2e leg (result read-back)
+    sp2 = stream2.cuda_stream
+
+    # ---- presampling epoch -> hotness -> (allreduce) -> hot order -> shards ---------------
+    t_pre = time.perf_counter()
+    for step in range(train_steps):
+        r.batch_generate(L.MODE_TRAIN, B, step, stream=lp[step % NL], pipe=step % NL)
+        r.run_batch(with_features=False, is_presc=True, stream=lp[step % NL])
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t_pre
+    nh, _th = r.hotness()
+    if world > 1:   # the path's one collective: NCCL allreduce of the hotness histogram (replaces aggregate_access)
+        class _W:   # zero-copy torch view of the library's device array
+            def __init__(s, ptr, n): s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_W(nh.ptr, N), device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    order = L.hot_order(nh)
+    kg = world
+    n_cached = int(N * args.cache_frac)
+    cap = max(1, (n_cached + kg - 1) // kg)
+    slot_of = L.place(order, cap, kg)
+    base = ds.features
+    host_tier = None
+    if args.cache_frac < 1.0:      # misses come from pinned host memory over UVA (reference default placement)
+        host_tier = L.MappedHostArray((N, D), np.float32)
+        torch.from_numpy(host_tier.array).copy_(ds.features.cpu())
+        base = host_tier
+    r.bind_features(base)
+    my_shard = L.fill_feature_shard(order, cap, kg, rank, ds.features, D)
+    shards = [my_shard]
+    imported = []
+    if world > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads in the gather kernel
+        import ctypes as C
+        h = (C.c_uint8 * 64)()
+        L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(my_shard.ptr), h), "ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        shards = []
+        for j in range(world):
+            if j == rank:
+                shards.append(my_shard)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(handles[j])
+            L._lib.check(L.lib().lgn_ipc_import(hb, C.byref(p)), "ipc_import")
+            imported.append(p)
+            shards.append(L.DevArray((cap, D), np.float32, ptr=p.value, owner=False))
+    r.bind_feature_cache(shards, slot_of, cap)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- the timed step -------------------------------------------------------------------
+    def step_resident(i):
+        r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % NL], pipe=i % NL)
+        r.run_batch(with_features=True, stream=lp[i % NL])
+
+    seeds_pin = torch.empty((train_steps, B), dtype=torch.int32).pin_memory()
+    labels_pin = torch.empty((train_steps, B), dtype=torch.int32).pin_memory()
+    seeds_pin.copy_(my_train[:train_steps * B].view(train_steps, B).cpu())
+    labels_pin.copy_(my_labels[:train_steps * B].view(train_steps, B).cpu())
+
+    def step_e2e(i):
+        # double-buffered consumer (PIPELINE_DEPTH 2, like the reference's trainer handshake): enqueue batch i from
+        # pinned host seeds (H2D), then read batch i-1's result block (D2H + host sync) while batch i is in flight
+        j = i % train_steps
+        r.batch_from_host(seeds_pin[j], labels_pin[j], step=j, stream=lp[i % NL], pipe=i % NL)
+        r.run_batch(with_features=True, stream=lp[i % NL])
+        return r.read_counters(stream=sp2, pipe=(i + 1) % NL)          # oldest batch in flight
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host_ms = [0.0]
+
+    def timed(fn, K, W, profile=False):
+        for i in range(W):
+            fn(i)
+        barrier()
+        if profile:
+            r.profile_enable(K * 8 + 16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        h0 = time.perf_counter()
+        for i in range(W, W + K):
+            fn(i)
+        host_ms[0] = 1e3 * (time.perf_counter() - h0) / K
+        for q in range(NL):              # the timed region ends when every slot's last gather is done
+            r.wait_pipe(q, stream=sp)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = r.profile_collect() if profile else None
+        if profile:
+            r.profile_enable(0)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), prof
+
+    K, W = args.steps, max(args.warmup, 3)
+    if args.probe:
+        def ev_time(fn, n):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn(n)
+            for q in range(NL):
+                r.wait_pipe(q, stream=sp)
+            for x in lanes[1:]:
+                stream.wait_stream(x)
+            b.record(stream)
+            barrier()
+            return a.elapsed_time(b) / n
+        for nl in (1, 2, 4, 8):
+            if nl > NL:
+                break
+            def samp(n, nl=nl):
+                for i in range(n):
+                    r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % nl], pipe=i % nl)
+                    r.run_batch(with_features=False, stream=lp[i % nl])
+            samp(8); print(f"sampling only, {nl} lanes: {ev_time(samp, 40):.4f} ms/step", file=sys.stderr)
+        for nl in (1, 2, 4):
+            if nl > NL:
+                break
+            for q in range(nl):     # one sampled batch per lane, then gathers only
+                r.batch_generate(L.MODE_TRAIN, B, q, stream=lp[q], pipe=q)
+                r.run_batch(with_features=False, stream=lp[q])
+            def gath(n, nl=nl):
+                for i in range(n):
+                    r.pipe = i % nl
+                    L.lib().lgn_batch_buffers  # noqa
+                    r.select_pipe(i % nl)
+                    for seg in range(len(fanout) + 1):
+                        r.gather_segment(seg, stream=lp[i % nl])
+            gath(4); print(f"gather only, {nl} streams: {ev_time(gath, 40):.4f} ms/batch", file=sys.stderr)
+        def both(n):
+            for i in range(n):
+                step_resident(i)
+        both(8); print(f"full pipeline, {NL} lanes: {ev_time(both, 40):.4f} ms/step", file=sys.stderr)
+        if os.environ.get("LGN_NCU_RANGE"):       # ncu --replay-mode app-range: whole-range metrics under real concurrency
+            barrier()
+            torch.cuda.profiler.start()
+            both(40)
+            barrier()
+            torch.cuda.profiler.stop()
+            return
+        both(NL * 2)
+        barrier()
+        r.profile_enable(1024)
+        both(NL * 3)
+        barrier()
+        names = {0: "begin", 1: "sample", 2: "gather", 3: "end"}
+        for kind, pipe, a, b in r.profile_timeline():
+            print(f"lane {pipe} {names[kind]:7s} {1e3 * a:9.1f} -> {1e3 * b:9.1f} us  ({1e3 * (b - a):7.1f})", file=sys.stderr)
+        return
+    clocks = ClockSampler(local)
+    r.tier_counts(reset=True, stream=sp)
+    clocks.start()
+    ms_total, prof = timed(step_resident, K, W, profile=True)
+    clk = clocks.stop()
+    host_enqueue_ms = host_ms[0]
+    tiers = r.tier_counts(reset=True, stream=sp)
+    ms_plain, _ = timed(step_resident, K, W)          # same loop without the per-operator timing events
+    host_enqueue_plain_ms = host_ms[0]
+    ms_e2e, _ = timed(step_e2e, K, W)
+
+    # work done in the timed steps (deterministic: replay the same steps untimed and read the counters)
+    edges = rows = 0
+    seg_rows = np.zeros(len(fanout) + 1, np.int64)
+    hop_items, hop_edges, hop_new = np.zeros(len(fanout), np.int64), np.zeros(len(fanout), np.int64), np.zeros(len(fanout), np.int64)
+    for i in range(W, W + K):
+        step_resident(i)
+        nc, ec = r.read_counters(stream=sp)
+        edges += int(ec[0]); rows += int(nc[0])
+        prev_e = 0
+        for h in range(len(fanout) + 1):
+            seg_rows[h] += int(nc[4 + 2 * h])
+        for h in range(len(fanout)):
+            e_h = int(ec[3 + h]) - prev_e
+            hop_items[h] += B if h == 0 else hop_edges_prev
+            hop_edges[h] += e_h; hop_new[h] += int(nc[6 + 2 * h])
+            hop_edges_prev, prev_e = e_h, int(ec[3 + h])
+    assert r.status(stream=sp) == 0, "device-side capacity overflow"
+    tot = torch.tensor([edges, rows], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)
+    job_edges, job_rows = float(tot[0].item()), float(tot[1].item())
+
+    value = job_edges / (ms_total / 1e3)
+    e2e_value = job_edges / (ms_e2e / 1e3)
+    row_bytes = 4 * D
+    feat_gbps = job_rows * row_bytes / (ms_total / 1e3) / 1e9
+
+    # ---- roofline of the dominant kernel (feature gather), timed live with CUDA events ----
+    hbm_peak, peak_src = peaks()
+    ms_kind, calls = prof
+    gather_ms, gather_calls = ms_kind[2], calls[2]
+    alg_bytes = rows * (2 * row_bytes + 8)                   # 2r + 8 per unique row (this rank)
+    achieved = alg_bytes / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
+    samp_bytes = float(sum(16 * hop_items[h] + 12 * hop_edges[h] + 4 * hop_new[h] for h in range(len(fanout))))
+    tsum = max(1, sum(tiers))
+    h_local, h_peer, h_host = tiers[0] / tsum, tiers[1] / tsum, tiers[2] / tsum
+    nvl, pcie = 770.0, 55.0                                  # measured peer copy (B200_PROFILING.md) / PCIe Gen5 x16 payload
+    inv = h_local / (hbm_peak / 2) + h_peer / nvl + h_host / pcie
+    hitmix_roof = 1.0 / inv if inv > 0 else hbm_peak / 2   # payload GB/s per GPU
+    gather_payload = rows * row_bytes / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_gather_v4 (feature extraction)", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "launches": int(gather_calls), "avg_launch_us": 1e3 * gather_ms / max(1, gather_calls),
+                "algorithmic_bytes_per_row": 2 * row_bytes + 8,
+                "hit_mix": {"local": h_local, "peer": h_peer, "host": h_host, "payload_roof_GBps_per_gpu": hitmix_roof,
+                            "achieved_payload_GBps_per_gpu": gather_payload, "frac": gather_payload / hitmix_roof},
+                "sampler": {"ms_per_step": ms_kind[1] / K, "algorithmic_GBps": samp_bytes / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] else 0.0},
+                "share_of_step": {"gather_ms": gather_ms / K, "sample_ms": ms_kind[1] / K, "begin_ms": ms_kind[0] / K,
+                                  "end_ms": ms_kind[3] / K, "step_ms": ms_total / K, "note": "gather and sampling overlap on two streams"}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
+            "config": {"workload": f"{args.config} ogbn-products-shaped synthetic ({N} nodes, {ds.n_edges} edges, {D}-d), "
+                                   f"GraphSAGE fanout {fanout}, batch {B}/GPU, rng {args.rng}, cache_frac {args.cache_frac}, kg {kg}, {NL} batches in flight",
+                       "l2": "working set (feature shard %.2f GB + 9.8 MB slot table + 0.26 GB CSR) larger than the 126 MB L2; "
+                             "consecutive steps touch different rows" % (cap * row_bytes / 1e9),
+                       "global_batch": B * world, "train_steps_per_epoch": train_steps},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 128,
+                    "ms_per_step": ms_e2e / K,
+                    "note": "lgn_batch_from_host (pinned seeds+labels H2D) + lgn_run_batch + lgn_read_counters (D2H, sync) every step"},
+            "gpu_launches": int(K * (1 + 3 * len(fanout) + (len(fanout) + 1) + 1)),
+            "roofline": roofline,
+            "extra": {"feature_extract_GBps": feat_gbps, "unique_rows_per_step": rows / K, "edges_per_step": edges / K,
+                      "graphsage_dataloading_epoch_s": train_steps * ms_total / K / 1e3,
+                      "presampling_epoch_s": t_pre, "tier_rows": tiers,
+                      "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unprofiled": host_enqueue_plain_ms,
+                      "ms_per_step_unprofiled": ms_plain / K}}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        hd = L.synth.Dataset(indptr=ds.indptr.cpu().numpy(), indices=ds.indices.cpu().numpy(), features=ds.features.cpu().numpy(),
+                             train_ids=my_train.cpu().numpy(), dim=D)
+        eps, gb, n, cores, dt = cpu_leg(hd, cfg, args.cpu_seconds, 100000, O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD, 42)
+        line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n} batches of {B} seeds of the same workload in {dt:.1f} s (oracle, OpenMP)",
+                                "feature_extract_GBps": gb}
+    if rank == 0:
+        print(json.dumps(line))
+    for p in imported:
+        L.lib().lgn_ipc_close(p)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

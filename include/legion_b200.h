@@ -23,7 +23,8 @@ extern "C" {
 
 #define LGN_MAX_HOPS 5
 #define LGN_MAX_PARTS 8        /* MAX_DEVICE, CUDA_IPC_Service.cu:16 */
-#define LGN_PIPELINE_DEPTH 2   /* PIPELINE_DEPTH, CUDA_IPC_Service.cu:17 */
+#define LGN_PIPELINE_DEPTH 2   /* PIPELINE_DEPTH, CUDA_IPC_Service.cu:17: slots visible to the trainer */
+#define LGN_MAX_LANES 8        /* independent batch slots a context may own (>= LGN_PIPELINE_DEPTH) */
 
 enum {
     LGN_OK = 0,
@@ -82,7 +83,8 @@ typedef struct {
     uint64_t rng_seed;              /* philox key */
     int64_t max_feature_rows;       /* 0 = worst case B*(1+f1+f1*f2+..); reference: 1.2*max presampled ids */
     int32_t enable_hotness;         /* allocate the two u32[N] presampling histograms */
-    int32_t reserved;
+    int32_t n_lanes;                /* batch slots ("pipes"): 0 = LGN_PIPELINE_DEPTH (reference); more slots let
+                                       more mini-batches be in flight when no trainer throttles the server */
 } lgn_config;
 
 int lgn_create(const lgn_config* cfg, lgn_ctx** out);
@@ -127,6 +129,14 @@ int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);
 /* the whole GPURunner::RunOnce / RunPreSc DAG (Server.cu:284-328) on one stream pair:
  * sampling on `stream`, gathers on the context's second stream, joined at the end. */
 int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_presc);
+/* lgn_run_batch does not join the two streams: the next batch's sampling overlaps this batch's
+ * gathers (pipeline depth 2).  A slot's batch is complete when its event fires:
+ * lgn_wait_pipe makes `stream` wait for it (device side), lgn_sync_pipe blocks the host
+ * (the reference's busy-poll on the last operator event, Server.cu:318-323). */
+/* operator-by-operator calls act on the slot chosen by the last batch_generate / select */
+int lgn_select_pipe(lgn_ctx* ctx, int32_t pipe);
+int lgn_wait_pipe(lgn_ctx* ctx, void* stream, int32_t pipe);
+int lgn_sync_pipe(lgn_ctx* ctx, int32_t pipe);
 
 /* ------------------------------------------------------------------ results */
 typedef struct {
@@ -150,6 +160,15 @@ int lgn_read_counters(lgn_ctx* ctx, void* stream, int32_t pipe, int32_t nc[16], 
 int lgn_tier_counts(lgn_ctx* ctx, void* stream, int64_t out[3], int32_t reset);
 /* sticky device-side status: 0 or LGN_E_CAPACITY */
 int lgn_status(lgn_ctx* ctx, void* stream);
+
+/* CUDA-event timing of the operators (bench.py's live roofline): every operator call records an
+ * event pair on its own stream while enabled.  kinds: 0 batch begin, 1 sampling hop (3 kernels),
+ * 2 feature gather, 3 batch end.  collect() synchronises, sums and resets. */
+int lgn_profile_enable(lgn_ctx* ctx, int32_t max_records);
+int lgn_profile_collect(lgn_ctx* ctx, double ms_by_kind[4], int64_t calls_by_kind[4]);
+/* raw timeline: up to max_records rows of {kind, slot, begin_ms, end_ms} relative to the first record; returns
+ * the number of rows through *n_out.  Does not reset. */
+int lgn_profile_timeline(lgn_ctx* ctx, double* rows4, int32_t max_records, int32_t* n_out);
 
 /* ------------------------------------------------------------------ planner
  * presampling statistics and cache construction (GPUCache.cu:578-826). */

@@ -26,7 +26,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("part", C.c_int32), ("n_nodes", C.c_int64), ("feat_dim", C.c_int32),
                 ("batch_size", C.c_int32), ("n_hops", C.c_int32), ("fanout", C.c_int32 * MAX_HOPS),
                 ("rng_mode", C.c_int32), ("rng_seed", C.c_uint64), ("max_feature_rows", C.c_int64),
-                ("enable_hotness", C.c_int32), ("reserved", C.c_int32)]
+                ("enable_hotness", C.c_int32), ("n_lanes", C.c_int32)]
 
 
 class BatchView(C.Structure):

@@ -56,6 +56,48 @@ __device__ __forceinline__ void st_cs_u32(void* p, uint32_t v)
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- L2 residency control ---------------------------------------
+// The dedup map is touched at random ~5 times per sampled edge, the feature rows exactly once:
+// slot_map accesses carry an evict_last policy so the map stays in the 126 MB L2 while the
+// gathers stream through it with evict_first.
+__device__ __forceinline__ unsigned long long policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_min_keep(int32_t* p, int32_t v, unsigned long long pol)
+{
+    asm volatile("red.global.min.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int32_t ld_keep(const int32_t* p, unsigned long long pol)
+{
+    int32_t r;
+    asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_keep(int32_t* p, int32_t v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p, unsigned long long pol)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, uint4 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // ---- thrust::minstd_rand compatibility (Kernels.cu:402-405) ----------------
 // state after discard(z) from seed 1 is 48271^z mod (2^31-1); the next draw is
 // 48271^(z+1).  Mersenne modulus => fold instead of divide.

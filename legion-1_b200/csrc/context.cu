@@ -3,6 +3,7 @@
 // (Server.cu:167-364) and the extern "C" wrappers of Kernels.cu without their blocking
 // cudaMemcpy / malloc on the hot loop (Kernels.cu:605-625, GPUCache.cu:394-395).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -118,6 +119,7 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     if (cfg->n_nodes <= 0 || cfg->n_nodes > 0x7fffffffLL || cfg->feat_dim < 0 || cfg->batch_size <= 0) return LGN_E_ARG;
     if (cfg->n_hops < 0 || cfg->n_hops > LGN_MAX_HOPS || cfg->part < 0 || cfg->part >= LGN_MAX_PARTS) return LGN_E_ARG;
     if (cfg->rng_mode != LGN_RNG_MINSTD && cfg->rng_mode != LGN_RNG_PHILOX) return LGN_E_ARG;
+    if (cfg->n_lanes < 0 || cfg->n_lanes > LGN_MAX_LANES) return LGN_E_ARG;
     long long cap = cfg->batch_size, cur = cfg->batch_size, max_slots = 1;
     for (int h = 0; h < cfg->n_hops; h++) {             // Server.cu:184-196
         if (cfg->fanout[h] <= 0 || cfg->fanout[h] > 256) return LGN_E_ARG;
@@ -134,8 +136,18 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     c->capacity = cap;
     c->max_slots = max_slots;
     c->max_rows = cfg->max_feature_rows > 0 ? cfg->max_feature_rows : cap;
+    c->n_lanes = cfg->n_lanes > 0 ? cfg->n_lanes : LGN_PIPELINE_DEPTH;
     CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-    for (int p = 0; p < LGN_PIPELINE_DEPTH; p++) {      // CUDA_IPC_Service.cu:140-215
+    long long slots_total = 0;
+    {
+        long long cur2 = cfg->batch_size;
+        for (int h = 0; h < cfg->n_hops; h++) { c->slot_off[h] = slots_total; cur2 *= cfg->fanout[h]; slots_total += (cur2 + 15) / 16 * 16; }
+        for (int h = cfg->n_hops; h <= LGN_MAX_HOPS; h++) c->slot_off[h] = slots_total;
+    }
+    const long long n_status = ((max_slots + 1023) / 1024 + 1) * LGN_MAX_HOPS;   // >= tiles of any RESOLVE_TILE >= 1024
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int p = 0; p < c->n_lanes; p++) {      // CUDA_IPC_Service.cu:140-215, Server.cu:217-231
         lgn::Pipe& pp = c->pipe[p];
         CK(cudaMalloc(&pp.ids, cap * sizeof(int32_t)));
         CK(cudaMalloc(&pp.labels, (size_t)cfg->batch_size * sizeof(int32_t)));
@@ -146,28 +158,41 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         CK(cudaMemset(pp.nc, 0, 64));
         CK(cudaMemset(pp.ec, 0, 64));
         if (cfg->feat_dim > 0) CK(cudaMalloc(&pp.features, (size_t)c->max_rows * cfg->feat_dim * sizeof(float)));
+        CK(cudaMalloc(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.agg_src_ids, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.agg_dst_ids, cap * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.slot_val, (max_slots + 16) * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.scan_status, n_status * sizeof(unsigned long long)));
+        CK(cudaMalloc(&pp.scan_ticket, LGN_MAX_HOPS * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.state, sizeof(lgn::BatchState)));
+        CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
+        CK(cudaMalloc(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
+        int rc = fill_i32(pp.slot_map, lgn::EMPTY, cfg->n_nodes, 0);
+        if (rc) return rc;
+        // gathers run at the lowest priority so the latency-bound sampling kernels get SM slots first
+        CK(cudaStreamCreateWithPriority(&pp.gather_stream, cudaStreamNonBlocking, prio_lo));
+        for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&pp.ev_hop[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.ev_end, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming));
     }
-    CK(cudaMalloc(&c->slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));      // Server.cu:219-222
-    CK(cudaMalloc(&c->agg_src_ids, cap * sizeof(int32_t)));
-    CK(cudaMalloc(&c->agg_dst_ids, cap * sizeof(int32_t)));
-    CK(cudaMalloc(&c->slot_dst, (max_slots + 4) * sizeof(int32_t)));
-    const long long n_status = ((max_slots + 1023) / 1024 + 1) * LGN_MAX_HOPS;
-    CK(cudaMalloc(&c->scan_status, n_status * sizeof(unsigned long long)));
-    CK(cudaMalloc(&c->scan_ticket, LGN_MAX_HOPS * sizeof(int32_t)));
-    CK(cudaMalloc(&c->state, sizeof(lgn::BatchState)));
-    CK(cudaMemset(c->state, 0, sizeof(lgn::BatchState)));
-    CK(cudaMalloc(&c->seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
     if (cfg->enable_hotness) {                                                   // GPUCache.cu:256-261 (u64 there)
         CK(cudaMalloc(&c->node_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
         CK(cudaMalloc(&c->topo_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
         CK(cudaMemset(c->node_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
         CK(cudaMemset(c->topo_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
     }
-    int rc = fill_i32(c->slot_map, lgn::EMPTY, cfg->n_nodes, 0);
-    if (rc) return rc;
-    CK(cudaStreamCreateWithFlags(&c->gather_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&c->ev_hop[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    {
+        const char* gm = getenv("LGN_GATHER");
+        c->gather_mode = (gm && gm[0] == 'l') ? 0 : 1;
+        const char* gc = getenv("LGN_GATHER_CTAS");
+        c->gather_ctas_per_sm = gc ? atoi(gc) : 1;
+        if (c->gather_ctas_per_sm < 1) c->gather_ctas_per_sm = 1;
+        auto knob = [](const char* name, int dflt) { const char* v = getenv(name); int x = v ? atoi(v) : dflt; return x < 1 ? 1 : x; };
+        c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
+        c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
+        c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
+    }
     c->feat.my_part = cfg->part;
     CK(cudaDeviceSynchronize());
     *out = c;
@@ -179,17 +204,19 @@ int lgn_destroy(lgn_ctx* c)
     if (!c) return LGN_E_ARG;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    for (int p = 0; p < LGN_PIPELINE_DEPTH; p++) {
+    for (int p = 0; p < c->n_lanes; p++) {
         lgn::Pipe& pp = c->pipe[p];
         cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
         cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
+        cudaFree(pp.slot_map); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids); cudaFree(pp.slot_dst); cudaFree(pp.slot_val);
+        cudaFree(pp.scan_status); cudaFree(pp.scan_ticket); cudaFree(pp.state); cudaFree(pp.seed_stage);
+        if (pp.gather_stream) cudaStreamDestroy(pp.gather_stream);
+        for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
+        if (pp.ev_end) cudaEventDestroy(pp.ev_end);
+        if (pp.ev_done) cudaEventDestroy(pp.ev_done);
     }
-    cudaFree(c->slot_map); cudaFree(c->agg_src_ids); cudaFree(c->agg_dst_ids); cudaFree(c->slot_dst);
-    cudaFree(c->scan_status); cudaFree(c->scan_ticket); cudaFree(c->state); cudaFree(c->seed_stage);
     cudaFree(c->node_hotness); cudaFree(c->topo_hotness);
-    cudaStreamDestroy(c->gather_stream);
-    for (int i = 0; i < LGN_MAX_HOPS + 2; i++) cudaEventDestroy(c->ev_hop[i]);
-    cudaEventDestroy(c->ev_join);
+    lgn_profile_enable(c, 0);
     cudaGetLastError();
     delete c;
     return LGN_OK;
@@ -236,10 +263,70 @@ int lgn_bind_feature_cache(lgn_ctx* c, int32_t n_parts, const float* const* shar
     return LGN_OK;
 }
 
+// ---------------------------------------------------------------- operator timing
+struct ProfScope {
+    lgn_ctx* c; cudaStream_t s; int idx;
+    ProfScope(lgn_ctx* c_, cudaStream_t s_, int kind) : c(c_), s(s_), idx(-1)
+    {
+        if (c->prof_cap && c->prof_n < c->prof_cap) {
+            idx = c->prof_n++;
+            c->prof_kind[idx] = (signed char)kind;
+            c->prof_pipe[idx] = (signed char)c->cur_pipe;
+            cudaEventRecord(c->prof_ev[2 * idx], s);
+        }
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_ev[2 * idx + 1], s); }
+};
+
+int lgn_profile_enable(lgn_ctx* c, int32_t max_records)
+{
+    if (!c || max_records < 0) return LGN_E_ARG;
+    for (int i = 0; i < 2 * c->prof_cap; i++) cudaEventDestroy(c->prof_ev[i]);
+    delete[] c->prof_ev; delete[] c->prof_kind; delete[] c->prof_pipe;
+    c->prof_ev = nullptr; c->prof_kind = nullptr; c->prof_pipe = nullptr; c->prof_cap = c->prof_n = 0;
+    if (max_records == 0) return LGN_OK;
+    c->prof_ev = new cudaEvent_t[2 * (size_t)max_records];
+    c->prof_kind = new signed char[max_records];
+    c->prof_pipe = new signed char[max_records];
+    for (int i = 0; i < 2 * max_records; i++) CK(cudaEventCreate(&c->prof_ev[i]));
+    c->prof_cap = max_records;
+    return LGN_OK;
+}
+
+int lgn_profile_collect(lgn_ctx* c, double ms[4], int64_t calls[4])
+{
+    if (!c || !ms || !calls) return LGN_E_ARG;
+    for (int k = 0; k < 4; k++) { ms[k] = 0.0; calls[k] = 0; }
+    for (int i = 0; i < c->prof_n; i++) {
+        CK(cudaEventSynchronize(c->prof_ev[2 * i + 1]));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        ms[c->prof_kind[i] & 3] += t;
+        calls[c->prof_kind[i] & 3]++;
+    }
+    c->prof_n = 0;
+    return LGN_OK;
+}
+
+int lgn_profile_timeline(lgn_ctx* c, double* rows, int32_t max_records, int32_t* n_out)
+{
+    if (!c || !rows || !n_out) return LGN_E_ARG;
+    int n = c->prof_n < max_records ? c->prof_n : max_records;
+    for (int i = 0; i < n; i++) {
+        CK(cudaEventSynchronize(c->prof_ev[2 * i + 1]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c->prof_ev[0], c->prof_ev[2 * i]));
+        CK(cudaEventElapsedTime(&b, c->prof_ev[0], c->prof_ev[2 * i + 1]));
+        rows[4 * i] = c->prof_kind[i]; rows[4 * i + 1] = c->prof_pipe[i]; rows[4 * i + 2] = a; rows[4 * i + 3] = b;
+    }
+    *n_out = n;
+    return LGN_OK;
+}
+
 // ---------------------------------------------------------------- hot path
 int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int32_t batch_size, int32_t counter)
 {
-    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH || mode < 0 || mode > 2 || batch_size <= 0 || counter < 0) return LGN_E_ARG;
+    if (!c || pipe < 0 || pipe >= c->n_lanes || mode < 0 || mode > 2 || batch_size <= 0 || counter < 0) return LGN_E_ARG;
     if (batch_size > c->cfg.batch_size) return LGN_E_CAPACITY;
     if (!c->seed_ids[mode]) return LGN_E_STATE;
     const int32_t total = c->seed_count[mode];
@@ -248,6 +335,8 @@ int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int
     if (size < 0) size = 0;
     const long long off = size * counter;
     c->cur_pipe = pipe;
+    if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent((cudaStream_t)stream, c->pipe[pipe].ev_done, 0));   // slot reuse (WAR)
+    ProfScope prof(c, (cudaStream_t)stream, 0);
     launch_batch_begin(c, (cudaStream_t)stream, c->seed_ids[mode], c->seed_labels[mode], (int32_t)off, (int32_t)size, (uint32_t)counter);
     CK(cudaGetLastError());
     return LGN_OK;
@@ -255,13 +344,16 @@ int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int
 
 int lgn_batch_from_host(lgn_ctx* c, void* stream, int32_t pipe, const int32_t* seeds, const int32_t* labels, int32_t count, uint32_t step)
 {
-    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH || count < 0 || (count > 0 && !seeds)) return LGN_E_ARG;
+    if (!c || pipe < 0 || pipe >= c->n_lanes || count < 0 || (count > 0 && !seeds)) return LGN_E_ARG;
     if (count > c->cfg.batch_size) return LGN_E_CAPACITY;
     cudaStream_t s = (cudaStream_t)stream;
     c->cur_pipe = pipe;
-    if (count > 0) CK(cudaMemcpyAsync(c->seed_stage, seeds, (size_t)count * 4, cudaMemcpyHostToDevice, s));
-    if (count > 0 && labels) CK(cudaMemcpyAsync(c->seed_stage + c->cfg.batch_size, labels, (size_t)count * 4, cudaMemcpyHostToDevice, s));
-    launch_batch_begin(c, s, c->seed_stage, labels ? c->seed_stage + c->cfg.batch_size : nullptr, 0, count, step);
+    if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent(s, c->pipe[pipe].ev_done, 0));   // slot reuse (WAR)
+    int32_t* stage = c->pipe[pipe].seed_stage;
+    if (count > 0) CK(cudaMemcpyAsync(stage, seeds, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+    if (count > 0 && labels) CK(cudaMemcpyAsync(stage + c->cfg.batch_size, labels, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+    ProfScope prof(c, s, 0);
+    launch_batch_begin(c, s, stage, labels ? stage + c->cfg.batch_size : nullptr, 0, count, step);
     CK(cudaGetLastError());
     return LGN_OK;
 }
@@ -271,6 +363,7 @@ int lgn_sample_hop(lgn_ctx* c, void* stream, int32_t hop, int32_t is_presc)
     if (!c || hop < 0 || hop >= c->cfg.n_hops) return LGN_E_ARG;
     if (!c->topo.base_indptr) return LGN_E_STATE;
     if (is_presc && !c->topo_hotness) return LGN_E_STATE;
+    ProfScope prof(c, (cudaStream_t)stream, 1);
     launch_sample_hop(c, (cudaStream_t)stream, hop, is_presc != 0);
     CK(cudaGetLastError());
     return LGN_OK;
@@ -280,6 +373,7 @@ int lgn_gather_segment(lgn_ctx* c, void* stream, int32_t segment)
 {
     if (!c || segment < 0 || segment > c->cfg.n_hops) return LGN_E_ARG;
     if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
+    ProfScope prof(c, (cudaStream_t)stream, 2);
     launch_gather(c, (cudaStream_t)stream, segment);
     CK(cudaGetLastError());
     return LGN_OK;
@@ -289,59 +383,99 @@ int lgn_finish_batch(lgn_ctx* c, void* stream, int32_t is_presc)
 {
     if (!c) return LGN_E_ARG;
     if (is_presc && !c->node_hotness) return LGN_E_STATE;
+    ProfScope prof(c, (cudaStream_t)stream, 3);
     launch_batch_end(c, (cudaStream_t)stream, is_presc != 0);
     CK(cudaGetLastError());
     return LGN_OK;
 }
 
 // GPURunner::RunOnce / RunPreSc (Server.cu:284-328): sampling ops on `stream`, feature
-// extraction ops on the second stream, chained by events; the caller's stream joins at the end.
+// extraction ops on the second stream, chained by events.  Unlike the reference (which
+// busy-polls the last event before touching the next batch, Server.cu:318-323) the caller's
+// stream is NOT joined here: the next batch's sampling overlaps this batch's gathers, the
+// slot's completion is the event lgn_wait_pipe / lgn_read_counters wait on.
 int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_presc)
 {
     if (!c) return LGN_E_ARG;
-    cudaStream_t s = (cudaStream_t)stream, g = c->gather_stream;
+    lgn::Pipe& pp = c->pipe[c->cur_pipe];
+    cudaStream_t s = (cudaStream_t)stream, g = pp.gather_stream;
     const bool feats = with_features && !is_presc && c->feat.base && c->cfg.feat_dim > 0;
     if (with_features && !is_presc && !feats) return LGN_E_STATE;
     int rc;
     if (feats) {
-        CK(cudaEventRecord(c->ev_hop[0], s));
-        CK(cudaStreamWaitEvent(g, c->ev_hop[0], 0));
+        CK(cudaEventRecord(pp.ev_hop[0], s));
+        CK(cudaStreamWaitEvent(g, pp.ev_hop[0], 0));
         if ((rc = lgn_gather_segment(c, g, 0))) return rc;
     }
     for (int h = 0; h < c->cfg.n_hops; h++) {
         if ((rc = lgn_sample_hop(c, s, h, is_presc))) return rc;
         if (feats) {
-            CK(cudaEventRecord(c->ev_hop[h + 1], s));
-            CK(cudaStreamWaitEvent(g, c->ev_hop[h + 1], 0));
+            CK(cudaEventRecord(pp.ev_hop[h + 1], s));
+            CK(cudaStreamWaitEvent(g, pp.ev_hop[h + 1], 0));
             if ((rc = lgn_gather_segment(c, g, h + 1))) return rc;
         }
     }
     if ((rc = lgn_finish_batch(c, s, is_presc))) return rc;
-    if (feats) {
-        CK(cudaEventRecord(c->ev_join, g));
-        CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+    if (feats) {   // slot complete = last gather done AND batch end done
+        CK(cudaEventRecord(pp.ev_end, s));
+        CK(cudaStreamWaitEvent(g, pp.ev_end, 0));
+        CK(cudaEventRecord(pp.ev_done, g));
+    } else {
+        CK(cudaEventRecord(pp.ev_done, s));
     }
+    pp.pending = true;
+    return LGN_OK;
+}
+
+int lgn_select_pipe(lgn_ctx* c, int32_t pipe)
+{
+    if (!c || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
+    c->cur_pipe = pipe;
+    return LGN_OK;
+}
+
+int lgn_wait_pipe(lgn_ctx* c, void* stream, int32_t pipe)
+{
+    if (!c || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
+    if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent((cudaStream_t)stream, c->pipe[pipe].ev_done, 0));
+    return LGN_OK;
+}
+
+int lgn_sync_pipe(lgn_ctx* c, int32_t pipe)
+{
+    if (!c || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
+    if (c->pipe[pipe].pending) CK(cudaEventSynchronize(c->pipe[pipe].ev_done));
     return LGN_OK;
 }
 
 // ---------------------------------------------------------------- results
 int lgn_batch_buffers(lgn_ctx* c, int32_t pipe, lgn_batch_view* v)
 {
-    if (!c || !v || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH) return LGN_E_ARG;
+    if (!c || !v || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
     const lgn::Pipe& p = c->pipe[pipe];
     v->ids = p.ids; v->features = p.features; v->labels = p.labels; v->agg_src = p.agg_src_off; v->agg_dst = p.agg_dst_off;
-    v->node_counter = p.nc; v->edge_counter = p.ec; v->agg_src_ids = c->agg_src_ids; v->agg_dst_ids = c->agg_dst_ids;
+    v->node_counter = p.nc; v->edge_counter = p.ec; v->agg_src_ids = p.agg_src_ids; v->agg_dst_ids = p.agg_dst_ids;
     v->capacity = c->capacity; v->max_rows = c->max_rows;
     return LGN_OK;
 }
 
 int lgn_read_counters(lgn_ctx* c, void* stream, int32_t pipe, int32_t nc[16], int32_t ec[16])
 {
-    if (!c || pipe < 0 || pipe >= LGN_PIPELINE_DEPTH) return LGN_E_ARG;
+    if (!c || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent(s, c->pipe[pipe].ev_done, 0));
     CK(cudaMemcpyAsync(nc, c->pipe[pipe].nc, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ec, c->pipe[pipe].ec, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return LGN_OK;
+}
+
+static int sync_lanes(lgn_ctx* c)
+{
+    for (int i = 0; i < c->n_lanes; i++) {
+        if (c->pipe[i].pending) CK(cudaEventSynchronize(c->pipe[i].ev_done));
+        CK(cudaStreamSynchronize(c->pipe[i].gather_stream));
+    }
     return LGN_OK;
 }
 
@@ -349,21 +483,32 @@ int lgn_tier_counts(lgn_ctx* c, void* stream, int64_t out[3], int32_t reset)
 {
     if (!c || !out) return LGN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long h[4];
-    CK(cudaMemcpyAsync(h, c->state->tier_rows, sizeof(h), cudaMemcpyDeviceToHost, s));
-    if (reset) CK(cudaMemsetAsync(c->state->tier_rows, 0, sizeof(h), s));
-    CK(cudaStreamSynchronize(s));
-    out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1]; out[2] = (int64_t)h[2];
+    int rc = sync_lanes(c);
+    if (rc) return rc;
+    out[0] = out[1] = out[2] = 0;
+    for (int i = 0; i < c->n_lanes; i++) {
+        unsigned long long h[4];
+        CK(cudaMemcpyAsync(h, c->pipe[i].state->tier_rows, sizeof(h), cudaMemcpyDeviceToHost, s));
+        if (reset) CK(cudaMemsetAsync(c->pipe[i].state->tier_rows, 0, sizeof(h), s));
+        CK(cudaStreamSynchronize(s));
+        out[0] += (int64_t)h[0]; out[1] += (int64_t)h[1]; out[2] += (int64_t)h[2];
+    }
     return LGN_OK;
 }
 
 int lgn_status(lgn_ctx* c, void* stream)
 {
     if (!c) return LGN_E_ARG;
-    int32_t st = 0;
-    CK(cudaMemcpyAsync(&st, &c->state->status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    return st;
+    int rc = sync_lanes(c);
+    if (rc) return rc;
+    int32_t worst = 0;
+    for (int i = 0; i < c->n_lanes; i++) {
+        int32_t st = 0;
+        CK(cudaMemcpyAsync(&st, &c->pipe[i].state->status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        if (st) worst = st;
+    }
+    return worst;
 }
 
 int lgn_hotness(lgn_ctx* c, uint32_t** node, uint32_t** topo)
@@ -377,10 +522,15 @@ int lgn_hotness(lgn_ctx* c, uint32_t** node, uint32_t** topo)
 int32_t lgn_max_ids(lgn_ctx* c, void* stream)
 {
     if (!c) return LGN_E_ARG;
-    int32_t v = 0;
-    if (cudaMemcpyAsync(&v, &c->state->max_ids, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return LGN_E_CUDA;
-    cudaStreamSynchronize((cudaStream_t)stream);
-    return v;
+    if (sync_lanes(c)) return LGN_E_CUDA;
+    int32_t best = 0;
+    for (int i = 0; i < c->n_lanes; i++) {
+        int32_t v = 0;
+        if (cudaMemcpyAsync(&v, &c->pipe[i].state->max_ids, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return LGN_E_CUDA;
+        cudaStreamSynchronize((cudaStream_t)stream);
+        if (v > best) best = v;
+    }
+    return best;
 }
 
 // ---------------------------------------------------------------- step arithmetic

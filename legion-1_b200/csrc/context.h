@@ -27,6 +27,10 @@ struct FeatView {
     int32_t n_parts;
 };
 
+// One pipeline slot = one independent lane: its own output buffers (the 7 IPC buffers of
+// CUDA_IPC_Service.cu:140-215), its own dedup map and scratch, its own gather stream.  Two
+// lanes let the latency-bound sampling chain of batch i+1 run while batch i is still in
+// flight (the reference shares one bitmap / position map and serialises batches).
 struct Pipe {
     int32_t* ids;
     float* features;
@@ -35,6 +39,21 @@ struct Pipe {
     int32_t* agg_dst_off;
     int32_t* nc;
     int32_t* ec;
+    // lane-private scratch
+    int32_t* slot_map;         // int32[N]
+    int32_t* agg_src_ids;      // raw ids, int32[capacity]
+    int32_t* agg_dst_ids;
+    int32_t* slot_dst;         // int32[sum of slots over hops]: draw results, then winners' local indices
+    int32_t* slot_val;         // int32[max slots of a hop]: slot_map value probed by k_mark
+    unsigned long long* scan_status;   // decoupled look-back tile descriptors
+    int32_t* scan_ticket;      // int32[LGN_MAX_HOPS]
+    BatchState* state;         // device
+    int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
+    cudaStream_t gather_stream;
+    cudaEvent_t ev_hop[LGN_MAX_HOPS + 2];
+    cudaEvent_t ev_end;        // batch_end enqueued on the sampling stream
+    cudaEvent_t ev_done;       // everything of the batch in this slot is complete
+    bool pending;
 };
 
 }  // namespace lgn
@@ -44,17 +63,10 @@ struct lgn_ctx {
     long long capacity;        // B*(1+f1+f1*f2+...)
     long long max_rows;
     long long max_slots;       // largest F_max*f over hops
-    lgn::Pipe pipe[LGN_PIPELINE_DEPTH];
+    lgn::Pipe pipe[LGN_MAX_LANES];
+    int n_lanes;
     int cur_pipe;
-    // scratch shared by the pipes
-    int32_t* slot_map;         // int32[N]
-    int32_t* agg_src_ids;      // raw ids, int32[capacity]
-    int32_t* agg_dst_ids;
-    int32_t* slot_dst;         // int32[max_slots]: uncompacted draw results of the current hop
-    unsigned long long* scan_status;   // decoupled look-back tile descriptors
-    int32_t* scan_ticket;      // int32[LGN_MAX_HOPS]
-    lgn::BatchState* state;    // device
-    int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
+    long long slot_off[LGN_MAX_HOPS + 1];   // start of hop h's region inside slot_dst
     uint32_t* node_hotness;    // u32[N] or NULL
     uint32_t* topo_hotness;
     // bound storage
@@ -63,11 +75,15 @@ struct lgn_ctx {
     int32_t seed_count[3];
     lgn::TopoView topo;
     lgn::FeatView feat;
-    // second stream + events for the sampling/gather overlap of Server.cu:301-328
-    cudaStream_t gather_stream;
-    cudaEvent_t ev_hop[LGN_MAX_HOPS + 2];
-    cudaEvent_t ev_join;
+    int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row
+    int gather_ctas_per_sm;
+    int sample_ctas_per_sm, resolve_ctas_per_sm, end_ctas_per_sm;   // grid caps (CTAs per SM) of the persistent kernels
     int n_sm;
+    // optional operator timing (lgn_profile_enable)
+    cudaEvent_t* prof_ev;      // 2 events per record
+    signed char* prof_kind;
+    signed char* prof_pipe;
+    int prof_cap, prof_n;
 };
 
 namespace lgn {

@@ -29,12 +29,16 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_const
     const int n_warps = (gridDim.x * GATHER_THREADS) >> 5;
     const int nvec = dim >> 2;
     unsigned long long n_local = 0, n_peer = 0, n_host = 0;
+    const unsigned long long stream_pol = policy_evict_first();   // rows are touched once: do not displace the dedup maps
+    // rows per warp-chunk: 32 for big segments, fewer for small ones so every warp gets work
+    int chunk = (cnt + n_warps - 1) / n_warps;
+    chunk = chunk >= 32 ? 32 : (chunk <= GATHER_UNROLL ? GATHER_UNROLL : ((chunk + GATHER_UNROLL - 1) / GATHER_UNROLL) * GATHER_UNROLL);
 
-    for (int r0 = warp * 32; r0 < cnt; r0 += n_warps * 32) {
+    for (int r0 = warp * chunk; r0 < cnt; r0 += n_warps * chunk) {
         // lane l: tier + source pointer of row r0+l
         const int r = r0 + lane;
         const uint4* src = nullptr;
-        if (r < cnt && (long long)(off + r) < max_rows) {
+        if (lane < chunk && r < cnt && (long long)(off + r) < max_rows) {
             const int32_t id = (int32_t)ld_nc_u32(ids + off + r);
             if (id >= 0) {                                        // Kernels.cu:694
                 const long long nid = id < n_nodes ? id : id % n_nodes;
@@ -49,10 +53,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_const
                     if (part == fv.my_part) n_local++; else n_peer++;
                 }
             }
-        } else if (r < cnt) {
+        } else if (lane < chunk && r < cnt) {
             st->status = LGN_E_CAPACITY;                          // reference: silent overflow (Server.cu:275)
         }
-        const int rows = min(32, cnt - r0);
+        const int rows = min(chunk, cnt - r0);
         uint4* dst0 = reinterpret_cast<uint4*>(out + (long long)(off + r0) * dim);
         for (int rr = 0; rr < rows; rr += GATHER_UNROLL) {
             uint4 v[GATHER_UNROLL][VEC];
@@ -66,15 +70,99 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_const
             for (int u = 0; u < GATHER_UNROLL; u++)
 #pragma unroll
                 for (int k = 0; k < VEC; k++)
-                    if (sp[u] && lane + 32 * k < nvec) v[u][k] = ld_nc_v4(sp[u] + lane + 32 * k);
+                    if (sp[u] && lane + 32 * k < nvec) v[u][k] = ld_stream_v4(sp[u] + lane + 32 * k, stream_pol);
 #pragma unroll
             for (int u = 0; u < GATHER_UNROLL; u++)
 #pragma unroll
                 for (int k = 0; k < VEC; k++)
-                    if (sp[u] && lane + 32 * k < nvec) st_cs_v4(dst0 + (long long)(rr + u) * nvec + lane + 32 * k, v[u][k]);
+                    if (sp[u] && lane + 32 * k < nvec) st_stream_v4(dst0 + (long long)(rr + u) * nvec + lane + 32 * k, v[u][k], stream_pol);
         }
     }
     // tier statistics for the hit-mix roofline: one atomic per warp per tier
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_local += __shfl_xor_sync(0xffffffffu, n_local, o);
+        n_peer += __shfl_xor_sync(0xffffffffu, n_peer, o);
+        n_host += __shfl_xor_sync(0xffffffffu, n_host, o);
+    }
+    if (lane == 0) {
+        if (n_local) atomicAdd(&st->tier_rows[0], n_local);
+        if (n_peer) atomicAdd(&st->tier_rows[1], n_peer);
+        if (n_host) atomicAdd(&st->tier_rows[2], n_host);
+    }
+}
+
+// ---- bulk-copy (TMA) variant ------------------------------------------------------------
+// One thread per row: the thread resolves its row's tier, then the copy engine moves the row
+// global -> shared (cp.async.bulk + mbarrier complete_tx) and shared -> global
+// (cp.async.bulk ... bulk_group).  Row bytes never pass through registers, a CTA keeps
+// blockDim rows in flight with ~30 registers per thread, so the kernel leaves most of each
+// SM to the sampling kernels of the next batch that run concurrently.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_constant__ FeatView fv,
+                                                                const int32_t* __restrict__ ids,
+                                                                const int32_t* __restrict__ nc, int seg_slot,
+                                                                float* __restrict__ out, int dim, long long n_nodes,
+                                                                long long max_rows, BatchState* __restrict__ st)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t row_bytes = (uint32_t)dim * 4u;                       // multiple of 16 (checked by the launcher)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)blockDim.x * row_bytes);
+    const uint32_t my_buf = smem_u32(smem + (size_t)t * row_bytes);
+    const uint32_t my_bar = smem_u32(bars + t);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(my_bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    unsigned long long n_local = 0, n_peer = 0, n_host = 0;
+    const unsigned long long stream_pol = policy_evict_first();
+    uint32_t phase = 0;
+    const int stride = gridDim.x * blockDim.x;
+    auto resolve = [&](int r) -> const float* {
+        if (r >= cnt) return nullptr;
+        if ((long long)(off + r) >= max_rows) { st->status = LGN_E_CAPACITY; return nullptr; }
+        const int32_t id = (int32_t)ld_nc_u32(ids + off + r);
+        if (id < 0) return nullptr;
+        const long long nid = id < n_nodes ? id : id % n_nodes;
+        int32_t g = -1;
+        if (fv.slot_of) g = (int32_t)ld_nc_u32(fv.slot_of + nid);
+        if (g < 0) { n_host++; return fv.base + nid * dim; }
+        const int part = (int)(g / fv.cap);
+        if (part == fv.my_part) n_local++; else n_peer++;
+        return fv.shard_tab[part] + (g - part * fv.cap) * dim;
+    };
+    int r = blockIdx.x * blockDim.x + t;
+    const float* src = resolve(r);
+    while (r < cnt) {
+        const int rn = r + stride;
+        // the bulk store that last read this thread's staging row must have drained
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (src) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_bar), "r"(row_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(my_buf), "l"(src), "r"(row_bytes), "r"(my_bar), "l"(stream_pol) : "memory");
+        }
+        const float* src_next = resolve(rn);        // next row's lookups fly while this row's copy lands
+        if (src) {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(my_bar), "r"(phase) : "memory");
+            }
+            phase ^= 1u;
+            float* dst = out + (long long)(off + r) * dim;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         ::"l"(dst), "r"(my_buf), "r"(row_bytes), "l"(stream_pol) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        r = rn;
+        src = src_next;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_local += __shfl_xor_sync(0xffffffffu, n_local, o);
@@ -147,14 +235,22 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment)
     const int blocks = c->n_sm * 8;   // 2048 threads / SM, grid-stride over 32-row chunks
     FeatView fv = c->feat;
     const int nvec = dim >> 2;
-    if (vec && nvec <= 32)
-        k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+    if (vec && c->gather_mode == 1) {
+        // staging rows + one mbarrier per thread; keep <= ~100 KB per CTA so two CTAs (or the sampler) fit beside it
+        int threads = GATHER_THREADS;
+        while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
+        const size_t smem = (size_t)threads * (dim * 4 + 8);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+    } else if (vec && nvec <= 32)
+        k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 64)
-        k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+        k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 128)
-        k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+        k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else
-        k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, c->state);
+        k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
 }
 
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,

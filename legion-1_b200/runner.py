@@ -21,14 +21,15 @@ def _ptr(x):
 
 class Runner:
     def __init__(self, n_nodes, feat_dim, batch_size, fanout, device=0, part=0, rng_mode=_lib.RNG_PHILOX,
-                 rng_seed=0, max_feature_rows=0, enable_hotness=False):
+                 rng_seed=0, max_feature_rows=0, enable_hotness=False, n_lanes=0):
         cfg = _lib.Config()
         cfg.device, cfg.part, cfg.n_nodes, cfg.feat_dim = device, part, n_nodes, feat_dim
         cfg.batch_size, cfg.n_hops = batch_size, len(fanout)
         for i, f in enumerate(fanout):
             cfg.fanout[i] = f
         cfg.rng_mode, cfg.rng_seed = rng_mode, rng_seed
-        cfg.max_feature_rows, cfg.enable_hotness = max_feature_rows, int(enable_hotness)
+        cfg.max_feature_rows, cfg.enable_hotness, cfg.n_lanes = max_feature_rows, int(enable_hotness), n_lanes
+        self.n_lanes = n_lanes or _lib.PIPELINE_DEPTH
         self.cfg = cfg
         self.fanout = list(fanout)
         self.handle = C.c_void_p()
@@ -95,6 +96,16 @@ class Runner:
         """GPURunner::RunOnce / RunPreSc minus the IPC handshake (Server.cu:284-328)."""
         check(lib().lgn_run_batch(self.handle, _vp(stream), int(with_features), int(is_presc)), "lgn_run_batch")
 
+    def select_pipe(self, pipe):
+        self.pipe = pipe
+        check(lib().lgn_select_pipe(self.handle, pipe), "lgn_select_pipe")
+
+    def wait_pipe(self, pipe, stream=None):
+        check(lib().lgn_wait_pipe(self.handle, _vp(stream), pipe), "lgn_wait_pipe")
+
+    def sync_pipe(self, pipe):
+        check(lib().lgn_sync_pipe(self.handle, pipe), "lgn_sync_pipe")
+
     # ---- results ------------------------------------------------------------------
     def view(self, pipe=None):
         v = _lib.BatchView()
@@ -142,6 +153,21 @@ class Runner:
 
     def max_ids(self, stream=None):
         return lib().lgn_max_ids(self.handle, _vp(stream))
+
+    def profile_enable(self, max_records):
+        check(lib().lgn_profile_enable(self.handle, C.c_int32(max_records)), "lgn_profile_enable")
+
+    def profile_collect(self):
+        ms = (C.c_double * 4)()
+        calls = (C.c_int64 * 4)()
+        check(lib().lgn_profile_collect(self.handle, ms, calls), "lgn_profile_collect")
+        return list(ms), list(calls)
+
+    def profile_timeline(self, max_records=4096):
+        rows = (C.c_double * (4 * max_records))()
+        n = C.c_int32()
+        check(lib().lgn_profile_timeline(self.handle, rows, max_records, C.byref(n)), "lgn_profile_timeline")
+        return [(int(rows[4 * i]), int(rows[4 * i + 1]), rows[4 * i + 2], rows[4 * i + 3]) for i in range(n.value)]
 
     def close(self):
         if self.handle:

@@ -127,7 +127,7 @@ def _scatter_mult(n_nodes):
     return m
 
 
-def calibrate_dmin(avg_deg, n_nodes, kmax=10, max_deg=10000, seed=SEED, sample=200_000):
+def calibrate_dmin(avg_deg, n_nodes, kmax=6, max_deg=10000, seed=SEED, sample=200_000):
     """bisection on the 16.16 fixed-point base degree so the mean degree of a
     deterministic sample of nodes matches avg_deg."""
     s = min(sample, n_nodes)
@@ -162,7 +162,7 @@ def features_block(xp, lo, hi, dim, device=None):
 
 
 def make_dataset(n_nodes, avg_deg, dim, n_class=47, backend="numpy", device=None, seed=SEED,
-                 kmax=10, max_deg=10000, with_features=True, chunk=1 << 24, dmin_fp=None):
+                 kmax=6, max_deg=10000, with_features=True, chunk=1 << 24, dmin_fp=None):
     xp = _NP if backend == "numpy" else _TH
     if dmin_fp is None:
         dmin_fp = calibrate_dmin(avg_deg, n_nodes, kmax, max_deg, seed)
