@@ -212,6 +212,24 @@ int lgo_sample_batch(lgo_sample_args* a)
     return rc;
 }
 
+void lgo_draw_hop(const int64_t* indptr, const int32_t* indices, const int32_t* frontier, int64_t n_items,
+                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, int32_t* out_dst)
+{
+    lgo_sample_args a;
+    memset(&a, 0, sizeof(a));
+    a.rng_mode = rng_mode; a.rng_seed = rng_seed; a.step = step;
+    for (int64_t idx = 0; idx < n_items * f; idx++) {
+        int64_t i = idx / f; int32_t k = (int32_t)(idx % f);
+        int32_t src = frontier[i], dst = -1;
+        if (src >= 0) {
+            int64_t start = indptr[src];
+            int32_t deg = (int32_t)(indptr[src + 1] - start);
+            if (k < deg) dst = indices[start + draw(&a, hop, f, idx, k, deg)];
+        }
+        out_dst[idx] = dst;
+    }
+}
+
 /* ------------------------------------------------------------- planner */
 
 typedef struct { uint32_t c; int32_t id; } hot_pair;

@@ -83,6 +83,12 @@ typedef struct {
 
 int lgo_sample_batch(lgo_sample_args* a);
 
+/* the draw step alone for one hop over an explicit frontier (Kernels.cu:383-410):
+ * out_dst[i*f+k] = sampled neighbour or -1.  Lets tests replay the reference's own (atomic-
+ * arrival) frontier order, on which its hop>=2 draws depend through idx. */
+void lgo_draw_hop(const int64_t* indptr, const int32_t* indices, const int32_t* frontier, int64_t n_items,
+                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, int32_t* out_dst);
+
 /* ---- cache planning (GPUCache.cu:578-659, 88-108, 200-205) ------------ */
 /* order[i] = node of rank i under (count desc, id asc). */
 void lgo_hot_order(const uint32_t* counts, int64_t n, int32_t* order);

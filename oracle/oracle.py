@@ -137,6 +137,14 @@ class Sampler:
         return out
 
 
+def draw_hop(indptr, indices, frontier, f, rng_mode=RNG_MINSTD, rng_seed=0, hop=0, step=0):
+    frontier = np.ascontiguousarray(frontier, np.int32)
+    out = np.empty(len(frontier) * f, np.int32)
+    lib().lgo_draw_hop(_p(indptr), _p(indices), _p(frontier), C.c_int64(len(frontier)), C.c_int32(f), C.c_int32(rng_mode),
+                       C.c_uint64(rng_seed), C.c_uint32(hop), C.c_uint32(step), _p(out))
+    return out
+
+
 def hot_order(counts):
     counts = np.ascontiguousarray(counts, np.uint32)
     order = np.empty(len(counts), np.int32)
