@@ -192,6 +192,8 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
         c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
+        const char* sg = getenv("LGN_SHARED_GATHER");
+        c->shared_gather_stream = sg ? atoi(sg) : 0;
     }
     c->feat.my_part = cfg->part;
     CK(cudaDeviceSynchronize());
@@ -374,7 +376,7 @@ int lgn_gather_segment(lgn_ctx* c, void* stream, int32_t segment)
     if (!c || segment < 0 || segment > c->cfg.n_hops) return LGN_E_ARG;
     if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
     ProfScope prof(c, (cudaStream_t)stream, 2);
-    launch_gather(c, (cudaStream_t)stream, segment);
+    launch_gather(c, (cudaStream_t)stream, segment, 1);
     CK(cudaGetLastError());
     return LGN_OK;
 }
@@ -398,11 +400,13 @@ int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_pr
 {
     if (!c) return LGN_E_ARG;
     lgn::Pipe& pp = c->pipe[c->cur_pipe];
-    cudaStream_t s = (cudaStream_t)stream, g = pp.gather_stream;
+    cudaStream_t s = (cudaStream_t)stream, g = c->shared_gather_stream ? c->pipe[0].gather_stream : pp.gather_stream;
     const bool feats = with_features && !is_presc && c->feat.base && c->cfg.feat_dim > 0;
     if (with_features && !is_presc && !feats) return LGN_E_STATE;
     int rc;
-    if (feats) {
+    // feature extraction of the seeds is fused with hop 1's segment (two small, latency-bound gathers
+    // become one); with no hops at all the seeds are gathered alone
+    if (feats && c->cfg.n_hops == 0) {
         CK(cudaEventRecord(pp.ev_hop[0], s));
         CK(cudaStreamWaitEvent(g, pp.ev_hop[0], 0));
         if ((rc = lgn_gather_segment(c, g, 0))) return rc;
@@ -412,7 +416,9 @@ int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_pr
         if (feats) {
             CK(cudaEventRecord(pp.ev_hop[h + 1], s));
             CK(cudaStreamWaitEvent(g, pp.ev_hop[h + 1], 0));
-            if ((rc = lgn_gather_segment(c, g, h + 1))) return rc;
+            ProfScope prof(c, g, 2);
+            if (h == 0) launch_gather(c, g, 0, 2); else launch_gather(c, g, h + 1, 1);
+            CK(cudaGetLastError());
         }
     }
     if ((rc = lgn_finish_batch(c, s, is_presc))) return rc;

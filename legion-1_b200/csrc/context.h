@@ -77,6 +77,7 @@ struct lgn_ctx {
     lgn::FeatView feat;
     int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row
     int gather_ctas_per_sm;
+    int shared_gather_stream;  // 1: all slots' gathers run back to back on one stream (one saturates HBM already)
     int sample_ctas_per_sm, resolve_ctas_per_sm, end_ctas_per_sm;   // grid caps (CTAs per SM) of the persistent kernels
     int n_sm;
     // optional operator timing (lgn_profile_enable)
@@ -93,7 +94,7 @@ void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const in
 void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc);
 void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
 // gather.cu
-void launch_gather(lgn_ctx* c, cudaStream_t s, int segment);
+void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs);
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,
                      float* dst, int n_sm, cudaStream_t s);
 }  // namespace lgn

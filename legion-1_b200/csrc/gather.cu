@@ -19,11 +19,13 @@ constexpr int GATHER_UNROLL = 4;
 // VEC: 16-byte vectors per lane per row (1 covers D <= 128, 2 covers D <= 256, ...)
 template <int VEC>
 __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
-                                                              const int32_t* __restrict__ nc, int seg_slot,
+                                                              const int32_t* __restrict__ nc, int seg_slot, int n_segs,
                                                               float* __restrict__ out, int dim, long long n_nodes,
                                                               long long max_rows, BatchState* __restrict__ st)
 {
-    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];       // Kernels.cu:672-681
+    const int off = nc[seg_slot];                               // Kernels.cu:672-681; adjacent segments may be fused
+    int cnt = 0;
+    for (int q = 0; q < n_segs; q++) cnt += nc[seg_slot + 1 + 2 * q];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * GATHER_THREADS) >> 5;
@@ -102,12 +104,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_constant__ FeatView fv,
                                                                 const int32_t* __restrict__ ids,
-                                                                const int32_t* __restrict__ nc, int seg_slot,
+                                                                const int32_t* __restrict__ nc, int seg_slot, int n_segs,
                                                                 float* __restrict__ out, int dim, long long n_nodes,
                                                                 long long max_rows, BatchState* __restrict__ st)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];
+    const int off = nc[seg_slot];
+    int cnt = 0;
+    for (int q = 0; q < n_segs; q++) cnt += nc[seg_slot + 1 + 2 * q];
     const int t = threadIdx.x, lane = t & 31;
     const uint32_t row_bytes = (uint32_t)dim * 4u;                       // multiple of 16 (checked by the launcher)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)blockDim.x * row_bytes);
@@ -178,11 +182,13 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_con
 
 // scalar fallback: D not a multiple of 4 floats or a tier base not 16-byte aligned
 __global__ void __launch_bounds__(GATHER_THREADS) k_gather_scalar(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
-                                                                  const int32_t* __restrict__ nc, int seg_slot,
+                                                                  const int32_t* __restrict__ nc, int seg_slot, int n_segs,
                                                                   float* __restrict__ out, int dim, long long n_nodes,
                                                                   long long max_rows, BatchState* __restrict__ st)
 {
-    const int off = nc[seg_slot], cnt = nc[seg_slot + 1];
+    const int off = nc[seg_slot];
+    int cnt = 0;
+    for (int q = 0; q < n_segs; q++) cnt += nc[seg_slot + 1 + 2 * q];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * GATHER_THREADS) >> 5;
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_row_copy(const int32_t* __re
     }
 }
 
-void launch_gather(lgn_ctx* c, cudaStream_t s, int segment)
+void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
 {
     Pipe& p = c->pipe[c->cur_pipe];
     const int dim = c->cfg.feat_dim;
@@ -242,15 +248,15 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment)
         const size_t smem = (size_t)threads * (dim * 4 + 8);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-        k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+        k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     } else if (vec && nvec <= 32)
-        k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+        k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 64)
-        k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+        k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 128)
-        k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+        k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else
-        k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+        k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
 }
 
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,
