@@ -56,6 +56,8 @@ int lgn_host_free(void* host_ptr);
 int lgn_copy_h2d(void* dev_dst, const void* host_src, int64_t bytes);
 int lgn_copy_d2h(void* host_dst, const void* dev_src, int64_t bytes);
 int lgn_memset_d(void* dev_dst, int value, int64_t bytes);
+int lgn_copy_d2d(void* dev_dst, const void* dev_src, int64_t bytes);   /* any two devices (UVA) */
+int lgn_device_synchronize(void);
 /* all-pairs cudaDeviceEnablePeerAccess among the first n devices
  * (GPUGraphStore::EnableP2PAccess, GPUGraphStore.cu:145-168). */
 int lgn_enable_peer_access(int32_t n_devices);
@@ -89,6 +91,8 @@ typedef struct {
 
 int lgn_create(const lgn_config* cfg, lgn_ctx** out);
 int lgn_destroy(lgn_ctx* ctx);
+/* index of this GPU inside its NVLink clique, once the clique layout is known (PreSc's cache_agg_mode) */
+int lgn_set_part(lgn_ctx* ctx, int32_t part);
 /* B*(1+f1+f1*f2+...) : per-pipe id / edge buffer capacity (Server.cu:184-196). */
 int64_t lgn_capacity(const lgn_ctx* ctx);
 
@@ -173,7 +177,13 @@ int lgn_profile_timeline(lgn_ctx* ctx, double* rows4, int32_t max_records, int32
 /* ------------------------------------------------------------------ planner
  * presampling statistics and cache construction (GPUCache.cu:578-826). */
 int lgn_hotness(lgn_ctx* ctx, uint32_t** node_hotness_dev, uint32_t** topo_hotness_dev);
-int32_t lgn_max_ids(lgn_ctx* ctx, void* stream);  /* PreSCCacheController::MaxIdNum (GPUCache.cu:294-296) */
+int32_t lgn_max_ids(lgn_ctx* ctx, void* stream);
+/* frontier items expanded and edges sampled since the last reset: the analytic stand-in for the PCIe
+ * read-transaction counters the reference takes from Intel PCM (Server.cu:84-108, GPUCache.cu:675):
+ * one 64-byte transaction per indptr pair and per neighbour read over UVA. */
+int lgn_sampling_totals(lgn_ctx* ctx, void* stream, int64_t out[2], int32_t reset);
+/* dst[i] += src[i]; src may live on a peer GPU (aggregate_access, GPUCache.cu:44-48, 624-627) */
+int lgn_accumulate_u32(uint32_t* dst_dev, const uint32_t* src_dev, int64_t n, void* stream);  /* PreSCCacheController::MaxIdNum (GPUCache.cu:294-296) */
 /* order[i] = id of rank i under (count desc, id asc): CandidateSelection's
  * sort_by_key (GPUCache.cu:630-631). sorted_counts may be NULL. */
 int lgn_hot_order(const uint32_t* counts_dev, int64_t n, int32_t* order_dev, uint32_t* sorted_counts_dev, void* stream);

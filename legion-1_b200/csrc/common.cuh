@@ -31,6 +31,8 @@ struct BatchState {
     int32_t max_ids;        // max unique ids over presampled batches (GPUCache.cu:294-296)
     int32_t pad;
     unsigned long long tier_rows[4];   // local, peer, host rows gathered
+    unsigned long long tot_items;      // frontier items expanded since the last reset (every hop)
+    unsigned long long tot_edges;      // edges sampled since the last reset
 };
 
 // ---- cache-hinted 128-bit / 32-bit accesses (G13/G14 of the Blackwell guide) ----

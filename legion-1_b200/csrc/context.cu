@@ -60,6 +60,8 @@ int lgn_host_free(void* host) { CK(cudaFreeHost(host)); return LGN_OK; }
 int lgn_copy_h2d(void* d, const void* h, int64_t bytes) { CK(cudaMemcpy(d, h, (size_t)bytes, cudaMemcpyHostToDevice)); return LGN_OK; }
 int lgn_copy_d2h(void* h, const void* d, int64_t bytes) { CK(cudaMemcpy(h, d, (size_t)bytes, cudaMemcpyDeviceToHost)); return LGN_OK; }
 int lgn_memset_d(void* d, int v, int64_t bytes) { CK(cudaMemset(d, v, (size_t)bytes)); return LGN_OK; }
+int lgn_copy_d2d(void* d, const void* s, int64_t bytes) { CK(cudaMemcpy(d, s, (size_t)bytes, cudaMemcpyDefault)); return LGN_OK; }
+int lgn_device_synchronize(void) { CK(cudaDeviceSynchronize()); return LGN_OK; }
 
 int lgn_enable_peer_access(int32_t n)
 {
@@ -225,6 +227,14 @@ int lgn_destroy(lgn_ctx* c)
 }
 
 int64_t lgn_capacity(const lgn_ctx* c) { return c ? c->capacity : 0; }
+
+int lgn_set_part(lgn_ctx* c, int32_t part)
+{
+    if (!c || part < 0 || part >= LGN_MAX_PARTS) return LGN_E_ARG;
+    c->cfg.part = part;
+    c->feat.my_part = part;
+    return LGN_OK;
+}
 
 // ---------------------------------------------------------------- storage binding
 int lgn_bind_seeds(lgn_ctx* c, int32_t mode, const int32_t* ids, const int32_t* labels, int32_t count)
@@ -515,6 +525,35 @@ int lgn_status(lgn_ctx* c, void* stream)
         if (st) worst = st;
     }
     return worst;
+}
+
+int lgn_sampling_totals(lgn_ctx* c, void* stream, int64_t out[2], int32_t reset)
+{
+    if (!c || !out) return LGN_E_ARG;
+    int rc = sync_lanes(c);
+    if (rc) return rc;
+    out[0] = out[1] = 0;
+    for (int i = 0; i < c->n_lanes; i++) {
+        unsigned long long h[2];
+        CK(cudaMemcpyAsync(h, &c->pipe[i].state->tot_items, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        if (reset) CK(cudaMemsetAsync(&c->pipe[i].state->tot_items, 0, sizeof(h), (cudaStream_t)stream));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        out[0] += (int64_t)h[0]; out[1] += (int64_t)h[1];
+    }
+    return LGN_OK;
+}
+
+__global__ void k_accumulate_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+int lgn_accumulate_u32(uint32_t* dst, const uint32_t* src, int64_t n, void* stream)
+{
+    if (!dst || !src || n < 0) return LGN_E_ARG;
+    k_accumulate_u32<<<1184, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    CK(cudaGetLastError());
+    return LGN_OK;
 }
 
 int lgn_hotness(lgn_ctx* c, uint32_t** node, uint32_t** topo)

@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_assign(
             HopState nx;
             nx.n_items = n_e; nx.item_base = hs.edge_base; nx.node_base = hs.node_base + n_new; nx.edge_base = hs.edge_base + n_e;
             st->hop[hop + 1] = nx;
+            st->tot_items += (unsigned long long)hs.n_items;
+            st->tot_edges += (unsigned long long)n_e;
             if ((long long)nx.node_base > capacity || (long long)nx.edge_base > capacity) st->status = LGN_E_CAPACITY;
             nc[0] = nx.node_base; nc[1] = 0; nc[2] = n_e;
             nc[5 + 2 * hop] = hs.node_base; nc[6 + 2 * hop] = n_new;
