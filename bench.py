@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nodes", type=int, default=0, help="override node count (debug)")
+    ap.add_argument("--placement", default="sharded", choices=["sharded", "hybrid", "replicated"],
+                    help="feature cache over the N GPUs: reference round-robin partition | hot rows replicated + rest partitioned | all replicated")
+    ap.add_argument("--gpu-cache-gb", type=float, default=38.0, help="per-GPU feature-cache budget (legion_server.py default 38 GB)")
     ap.add_argument("--probe", action="store_true", help="debug: time sampling-only and gather-only loops")
     ap.add_argument("--lanes", type=int, default=4, help="mini-batches in flight per GPU (batch slots)")
     return ap.parse_args()
@@ -201,12 +204,10 @@ def run_b200(args):
     dmin = L.synth.calibrate_dmin(cfg["avg_deg"], N)
     ds = L.synth.make_dataset(N, cfg["avg_deg"], D, n_class=cfg["n_class"], backend="torch", device=dev, dmin_fp=dmin)
     torch.cuda.synchronize()
-    my_train = ds.train_ids[(ds.train_ids % world) == rank].contiguous()          # GPUGraphStore.cu:338
+    from legion_b200 import cluster
+    my_train = cluster.partition_seeds(ds.train_ids, world, rank).contiguous()        # GPUGraphStore.cu:338
     my_labels = ds.labels[my_train.long()].contiguous()
-    n_train = torch.tensor([my_train.numel()], device=dev)
-    if world > 1:
-        dist.all_reduce(n_train, op=dist.ReduceOp.MIN)
-    train_steps = (int(n_train.item()) - 1) // B                                    # CUDA_IPC_Service.cu:88
+    train_steps = cluster.train_steps(my_train.numel(), B, dist if world > 1 else None)    # CUDA_IPC_Service.cu:88
 
     r = L.Runner(N, D, B, fanout, device=local, part=rank, rng_mode=rng_mode, rng_seed=42, enable_hotness=True, n_lanes=args.lanes)
     r.bind_topology(ds.indptr, ds.indices)            # topology replicated in HBM (7 % of one B200 even for papers100M)
@@ -227,33 +228,40 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t_pre
     nh, _th = r.hotness()
-    if world > 1:   # the path's one collective: NCCL allreduce of the hotness histogram (replaces aggregate_access)
-        class _W:   # zero-copy torch view of the library's device array
-            def __init__(s, ptr, n): s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        t = torch.as_tensor(_W(nh.ptr, N), device=dev)
-        dist.all_reduce(t)
+    if world > 1:   # the path's one collective: NCCL all-reduce of the hotness histogram (replaces aggregate_access)
+        cluster.allreduce_hotness(dist, nh, n=N, device=dev)
         torch.cuda.synchronize()
     order = L.hot_order(nh)
     kg = world
+    row_bytes_ = 4 * D
     n_cached = int(N * args.cache_frac)
-    cap = max(1, (n_cached + kg - 1) // kg)
-    slot_of = L.place(order, cap, kg)
+    budget_rows = int(args.gpu_cache_gb * 1e9 // row_bytes_)
+    if args.placement == "replicated" or kg == 1:
+        n_repl = min(n_cached, budget_rows) if args.placement == "replicated" else 0
+    elif args.placement == "hybrid":      # replicate as many of the hottest rows as the budget allows, partition the rest
+        n_repl = max(0, min(n_cached, (budget_rows * kg - n_cached) // (kg - 1)))
+    else:
+        n_repl = 0
+    if args.placement == "replicated":
+        cap = max(1, n_repl)
+    else:
+        cap = n_repl + cluster.capacity_for(n_cached - n_repl, kg)
+    slot_of = L.place_hybrid(order, cap, kg, n_repl, rank)
     base = ds.features
     host_tier = None
-    if args.cache_frac < 1.0:      # misses come from pinned host memory over UVA (reference default placement)
+    if args.cache_frac < 1.0 or (args.placement == "replicated" and n_repl < N):   # misses: pinned host memory over UVA
         host_tier = L.MappedHostArray((N, D), np.float32)
         torch.from_numpy(host_tier.array).copy_(ds.features.cpu())
         base = host_tier
     r.bind_features(base)
-    my_shard = L.fill_feature_shard(order, cap, kg, rank, ds.features, D)
+    my_shard = L.fill_feature_shard_hybrid(order, cap, kg, rank, n_repl, ds.features, D)
     shards = [my_shard]
     imported = []
-    if world > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads in the gather kernel
+    if world > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
         import ctypes as C
         h = (C.c_uint8 * 64)()
         L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(my_shard.ptr), h), "ipc_export")
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(h))
+        handles = cluster.exchange_handles(dist, bytes(h))
         shards = []
         for j in range(world):
             if j == rank:
@@ -450,7 +458,8 @@ def run_b200(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
             "config": {"workload": f"{args.config} ogbn-products-shaped synthetic ({N} nodes, {ds.n_edges} edges, {D}-d), "
-                                   f"GraphSAGE fanout {fanout}, batch {B}/GPU, rng {args.rng}, cache_frac {args.cache_frac}, kg {kg}, {NL} batches in flight",
+                                   f"GraphSAGE fanout {fanout}, batch {B}/GPU, rng {args.rng}, cache_frac {args.cache_frac}, kg {kg}, placement {args.placement} ({n_repl} rows replicated), {NL} batches in flight",
+                       "parallelism": f"dp{world}: seeds tid%{world}, feature cache {args.placement} over {kg} GPU(s)",
                        "l2": "working set (feature shard %.2f GB + 9.8 MB slot table + 0.26 GB CSR) larger than the 126 MB L2; "
                              "consecutive steps touch different rows" % (cap * row_bytes / 1e9),
                        "global_batch": B * world, "train_steps_per_epoch": train_steps},

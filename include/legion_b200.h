@@ -192,6 +192,15 @@ int lgn_place(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int3
 /* shard j row r <- features[order[r*kg+j]] (FeatFillUp, GPUCache.cu:200-205) */
 int lgn_fill_feature_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j,
                            const float* features_dev, int32_t dim, float* shard_dev, void* stream);
+/* B200 extension (no reference counterpart): hybrid placement.  The n_repl hottest ranks are
+ * REPLICATED on every GPU of the clique (rows [0, n_repl) of each shard, served from local HBM), the next
+ * (cap - n_repl) * kg ranks are partitioned as above into rows [n_repl, cap).  n_repl = 0 is the reference
+ * placement; n_repl = cap replicates everything (the reference's cache_agg_mode 0).  The slot map differs per
+ * GPU: replicated ranks point at `my_part`. */
+int lgn_place_hybrid(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int64_t n_repl, int32_t my_part,
+                     int32_t* slot_of_dev, void* stream);
+int lgn_fill_feature_shard_hybrid(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j, int64_t n_repl,
+                                  const float* features_dev, int32_t dim, float* shard_dev, void* stream);
 /* topology shard j (GraphCache, GPU_Memory_Graph_Storage.cu:98-133). Pass
  * indices_out_dev = NULL to size it: *n_indices receives the count (host sync). */
 int lgn_fill_topo_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j,

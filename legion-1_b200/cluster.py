@@ -1,0 +1,69 @@
+"""One-process-per-GPU plumbing (torch.distributed): seed partitioning, the path's single collective
+(sum of the presampling hotness histograms, replacing aggregate_access, GPUCache.cu:44-48,624-647) and
+the one-off exchange of CUDA-IPC handles of the cache shards.  No compute happens here: device work
+stays behind the C-ABI; these helpers only move small host objects and call all_reduce on a tensor
+view of the library's histogram.  Works with backend "nccl" (GPU tensors) and "gloo" (CPU tests)."""
+import numpy as np
+
+
+def partition_seeds(ids, world, rank):
+    """seed `tid` belongs to partition `tid % P`, file order kept (GPUGraphStore.cu:332-346)."""
+    return ids[(ids % world) == rank]
+
+
+def train_steps(n_train_mine, batch, dist=None):
+    """train_step = (min_i n_train_i - 1) / B (CUDA_IPC_Service.cu:71-88): the minimum over ranks."""
+    n = int(n_train_mine)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        t = torch.tensor([n], dtype=torch.int64)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        n = int(t.item())
+    return (n - 1) // batch
+
+
+class _DeviceView:
+    """zero-copy int32 view of a device array for torch.as_tensor (counts stay < 2^31)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def allreduce_hotness(dist, hist, n=None, device=None):
+    """in-place sum over ranks.  `hist` is a torch tensor (CPU for gloo, CUDA for nccl) or a device
+    array object with .ptr owned by the library."""
+    import torch
+    if hasattr(hist, "ptr"):
+        t = torch.as_tensor(_DeviceView(hist.ptr, n), device=device)
+    else:
+        t = hist
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+def exchange_handles(dist, handle_bytes):
+    """every rank contributes its 64-byte CUDA-IPC handle; returns the list indexed by rank."""
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    if world == 1:
+        return [bytes(handle_bytes)]
+    out = [None] * world
+    dist.all_gather_object(out, bytes(handle_bytes))
+    return out
+
+
+def slot_of_rank(i, cap, kg):
+    """global slot of hot rank i: GPU i % kg, row i / kg (InitPair, GPUCache.cu:103-108)."""
+    return (i % kg) * cap + i // kg
+
+
+def shard_ranks(cap, kg, j, n):
+    """hot ranks stored on GPU j, in row order (FeatFillUp, GPUCache.cu:200-205)."""
+    r = np.arange(cap, dtype=np.int64) * kg + j
+    return r[r < n]
+
+
+def capacity_for(n_cached, kg):
+    return max(1, (int(n_cached) + kg - 1) // kg)

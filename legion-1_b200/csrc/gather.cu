@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_scalar(const __grid_c
 
 // shard fill: row r of shard j <- src[order[r*kg + j]] (FeatFillUp, GPUCache.cu:200-205)
 __global__ void __launch_bounds__(GATHER_THREADS) k_row_copy(const int32_t* __restrict__ order, long long n, long long cap,
-                                                             int kg, int j, const float* __restrict__ src, int dim,
+                                                             int kg, int j, long long n_repl, const float* __restrict__ src, int dim,
                                                              float* __restrict__ dst)
 {
     const int lane = threadIdx.x & 31;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_row_copy(const int32_t* __re
     const long long n_warps = ((long long)gridDim.x * GATHER_THREADS) >> 5;
     const bool vec = (dim & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
     for (long long r = warp; r < cap; r += n_warps) {
-        const long long rank = r * kg + j;
+        const long long rank = r < n_repl ? r : n_repl + (r - n_repl) * kg + j;   // replicated head, partitioned tail
         if (rank >= n) continue;
         const long long id = order[rank];
         if (vec) {
@@ -259,10 +259,10 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
         k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
 }
 
-void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, const float* src, int dim,
+void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,
                      float* dst, int n_sm, cudaStream_t s)
 {
-    k_row_copy<<<n_sm * 8, GATHER_THREADS, 0, s>>>(order, n, cap, kg, j, src, dim, dst);
+    k_row_copy<<<n_sm * 8, GATHER_THREADS, 0, s>>>(order, n, cap, kg, j, n_repl, src, dim, dst);
 }
 
 }  // namespace lgn

@@ -29,12 +29,16 @@ __global__ void k_iota(int32_t* p, long long n)
 
 // slot_of[id] = (i % kg) * cap + i / kg for hot rank i (InitPair, GPUCache.cu:103-108).
 // A direct-mapped table: one 4-byte probe per lookup instead of a cuckoo bucket walk.
-__global__ void k_place(const int32_t* __restrict__ order, long long n, long long cap, int kg, int32_t* __restrict__ slot_of)
+__global__ void k_place(const int32_t* __restrict__ order, long long n, long long cap, int kg, long long n_repl, int my_part,
+                        int32_t* __restrict__ slot_of)
 {
-    const long long lim = cap * kg < n ? cap * kg : n;
+    const long long lim = n_repl + (cap - n_repl) * kg;   // ranks that have a row somewhere in the clique
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int32_t id = order[i];
-        slot_of[id] = i < lim ? (int32_t)((i % kg) * cap + i / kg) : -1;
+        int32_t slot = -1;
+        if (i < n_repl) slot = (int32_t)(my_part * cap + i);                 // replicated: every GPU serves it locally
+        else if (i < lim) { const long long k = i - n_repl; slot = (int32_t)((k % kg) * cap + n_repl + k / kg); }
+        slot_of[id] = slot;
     }
 }
 
@@ -110,11 +114,30 @@ extern "C" int lgn_hot_order(const uint32_t* counts, int64_t n, int32_t* order, 
     return LGN_OK;
 }
 
-extern "C" int lgn_place(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t* slot_of, void* stream)
+extern "C" int lgn_place_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int64_t n_repl, int32_t my_part,
+                                int32_t* slot_of, void* stream)
 {
     if (!order || !slot_of || n <= 0 || kg <= 0 || kg > LGN_MAX_PARTS || cap < 0) return LGN_E_ARG;
+    if (n_repl < 0 || n_repl > cap || my_part < 0 || my_part >= kg) return LGN_E_ARG;
     if (cap * kg > 0x7fffffffLL) return LGN_E_ARG;   // reference overflows int32 here (GPUCache.cu:315)
-    k_place<<<1024, 256, 0, (cudaStream_t)stream>>>(order, n, cap, kg, slot_of);
+    k_place<<<1024, 256, 0, (cudaStream_t)stream>>>(order, n, cap, kg, n_repl, my_part, slot_of);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+extern "C" int lgn_place(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t* slot_of, void* stream)
+{
+    return lgn_place_hybrid(order, n, cap, kg, 0, 0, slot_of, stream);
+}
+
+extern "C" int lgn_fill_feature_shard_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j, int64_t n_repl,
+                                             const float* features, int32_t dim, float* shard, void* stream)
+{
+    if (!order || !features || !shard || kg <= 0 || j < 0 || j >= kg || dim <= 0 || n_repl < 0 || n_repl > cap) return LGN_E_ARG;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    launch_row_copy(order, n, cap, kg, j, n_repl, features, dim, shard, n_sm, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return LGN_OK;
 }
@@ -122,13 +145,7 @@ extern "C" int lgn_place(const int32_t* order, int64_t n, int64_t cap, int32_t k
 extern "C" int lgn_fill_feature_shard(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j,
                                       const float* features, int32_t dim, float* shard, void* stream)
 {
-    if (!order || !features || !shard || kg <= 0 || j < 0 || j >= kg || dim <= 0) return LGN_E_ARG;
-    int dev = 0, n_sm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    launch_row_copy(order, n, cap, kg, j, features, dim, shard, n_sm, (cudaStream_t)stream);
-    CK(cudaGetLastError());
-    return LGN_OK;
+    return lgn_fill_feature_shard_hybrid(order, n, cap, kg, j, 0, features, dim, shard, stream);
 }
 
 extern "C" int lgn_fill_topo_shard(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j,

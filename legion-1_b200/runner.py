@@ -205,6 +205,23 @@ def fill_feature_shard(order, cap, kg, j, features, dim, stream=None, out=None):
     return shard
 
 
+def place_hybrid(order, cap, kg, n_repl, my_part, stream=None):
+    """B200 extension: n_repl hottest ranks replicated on every GPU, the rest partitioned (lgn_place_hybrid)."""
+    n = order.shape[0]
+    slot_of = DevArray((n,), np.int32)
+    check(lib().lgn_place_hybrid(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int64(n_repl), C.c_int32(my_part),
+                                 _ptr(slot_of), _vp(stream)), "lgn_place_hybrid")
+    return slot_of
+
+
+def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features, dim, stream=None):
+    n = order.shape[0]
+    shard = DevArray.zeros((cap, dim), np.float32)
+    check(lib().lgn_fill_feature_shard_hybrid(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int32(j), C.c_int64(n_repl),
+                                              _ptr(features), C.c_int32(dim), _ptr(shard), _vp(stream)), "lgn_fill_feature_shard_hybrid")
+    return shard
+
+
 def fill_topo_shard(order, cap, kg, j, indptr, indices, stream=None):
     n = order.shape[0]
     ip = DevArray((cap + 1,), np.int64)

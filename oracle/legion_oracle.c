@@ -270,6 +270,27 @@ void lgo_fill_feature_shard(const int32_t* order, int64_t n, int64_t cap, int32_
     }
 }
 
+void lgo_place_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int64_t n_repl, int32_t my_part, int32_t* slot_of)
+{
+    int64_t lim = n_repl + (cap - n_repl) * kg;
+    for (int64_t i = 0; i < n; i++) {
+        int32_t slot = -1;
+        if (i < n_repl) slot = (int32_t)(my_part * cap + i);
+        else if (i < lim) { int64_t k = i - n_repl; slot = (int32_t)((k % kg) * cap + n_repl + k / kg); }
+        slot_of[order[i]] = slot;
+    }
+}
+
+void lgo_fill_feature_shard_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j, int64_t n_repl,
+                                   const float* features, int32_t dim, float* shard)
+{
+    for (int64_t r = 0; r < cap; r++) {
+        int64_t rank = r < n_repl ? r : n_repl + (r - n_repl) * kg + j;
+        if (rank >= n) continue;
+        memcpy(shard + r * dim, features + (int64_t)order[rank] * dim, (size_t)dim * sizeof(float));
+    }
+}
+
 int64_t lgo_fill_topo_shard(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j,
                             const int64_t* indptr, const int32_t* indices,
                             int64_t* indptr_out, int32_t* indices_out)

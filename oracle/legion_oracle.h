@@ -99,6 +99,11 @@ void lgo_place(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t
  * Rows whose rank is >= n are left untouched. */
 void lgo_fill_feature_shard(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j,
                             const float* features, int32_t dim, float* shard);
+/* hybrid placement (extension of this repo, no reference counterpart): the n_repl hottest ranks are replicated
+ * on every GPU (rows [0,n_repl)), the following (cap-n_repl)*kg ranks partitioned round-robin into rows [n_repl,cap). */
+void lgo_place_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int64_t n_repl, int32_t my_part, int32_t* slot_of);
+void lgo_fill_feature_shard_hybrid(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j, int64_t n_repl,
+                                   const float* features, int32_t dim, float* shard);
 /* shard j topology CSR of nodes order[t*Kg+j] (GetNeighborCount/TopoFillUp,
  * GPU_Memory_Graph_Storage.cu:14-35,98-133).  indptr_out int64[cap+1];
  * indices_out may be NULL to only size it.  Returns number of indices. */

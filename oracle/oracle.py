@@ -166,6 +166,20 @@ def fill_feature_shard(order, cap, kg, j, features):
     return shard
 
 
+def place_hybrid(order, cap, kg, n_repl, my_part):
+    slot = np.empty(len(order), np.int32)
+    lib().lgo_place_hybrid(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int64(n_repl), C.c_int32(my_part), _p(slot))
+    return slot
+
+
+def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features):
+    features = np.ascontiguousarray(features, np.float32)
+    shard = np.zeros((cap, features.shape[1]), np.float32)
+    lib().lgo_fill_feature_shard_hybrid(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j), C.c_int64(n_repl),
+                                        _p(features), C.c_int32(features.shape[1]), _p(shard))
+    return shard
+
+
 def fill_topo_shard(order, cap, kg, j, indptr, indices):
     ip = np.zeros(cap + 1, np.int64)
     n = lib().lgo_fill_topo_shard(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),

@@ -191,6 +191,52 @@ def test_gather_bit_exact(dim, kg, frac, host, gather, monkeypatch):
     r.close()
 
 
+@pytest.mark.parametrize("kg,frac_repl,frac_shard", [(4, 0.2, 0.5), (2, 1.0, 0.0), (8, 0.0, 1.0), (4, 0.1, 0.2)])
+def test_hybrid_placement_gather(kg, frac_repl, frac_shard):
+    """B200 extension: hottest ranks replicated on every GPU, warm ranks partitioned, cold ranks on the host tier.
+    Every emulated GPU of the clique (its own slot map + shard, peers addressed through the shard table) must
+    gather the same bit-exact rows; replicated rows must be served locally."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    dim = 100
+    d = L.synth.make_dataset(20_000, 10.0, dim, n_class=5)
+    rng = np.random.default_rng(1)
+    counts = rng.integers(0, 50, d.n_nodes).astype(np.uint32)
+    order_h = O.hot_order(counts)
+    n_repl = int(d.n_nodes * frac_repl)
+    cap = n_repl + int(np.ceil(d.n_nodes * frac_shard / kg))
+    base = L.MappedHostArray.from_numpy(d.features)
+    order_d = L.hot_order(L.DevArray.from_numpy(counts))
+    shards_h = [O.fill_feature_shard_hybrid(order_h, cap, kg, j, n_repl, d.features) for j in range(kg)]
+    shards_d = [L.fill_feature_shard_hybrid(order_d, cap, kg, j, n_repl, base, dim) for j in range(kg)]
+    for j in range(kg):
+        assert np.array_equal(shards_d[j].numpy().view(np.uint32), shards_h[j].view(np.uint32))
+    fanout, B = [10, 5], 512
+    smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=3)
+    seeds = d.train_ids[:B]
+    want = smp.sample(seeds, step=0)
+    total = int(want["nc"][0])
+    for me in range(0, kg, max(1, kg // 2)):
+        slot_h = O.place_hybrid(order_h, cap, kg, n_repl, me)
+        slot_d = L.place_hybrid(order_d, cap, kg, n_repl, me)
+        assert np.array_equal(slot_d.numpy(), slot_h)
+        r = L.Runner(d.n_nodes, dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=3, part=me)
+        r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+        r.bind_features(base)
+        r.bind_feature_cache(shards_d, slot_d, cap)
+        r.batch_from_host(seeds, None, step=0)
+        r.run_batch(with_features=True)
+        got = r.fetch()
+        assert np.array_equal(got["features"].view(np.uint32), d.features[want["sampled_ids"][:total]].view(np.uint32))
+        ref = np.zeros((total, dim), np.float32)
+        tiers = O.gather(want["sampled_ids"], 0, total, slot_h, cap, shards_h, d.features, ref, tiers=True)
+        tc = r.tier_counts()
+        assert tc == [int(tiers[me]), int(tiers[:kg].sum() - tiers[me]), int(tiers[kg])]
+        hot = np.isin(want["sampled_ids"][:total], order_h[:n_repl]).sum()
+        assert tc[0] >= hot                                                  # every replicated row was a local hit
+        r.close()
+
+
 def test_presampling_hotness_and_planner(c1):
     """presampling epoch: node / topology hotness, max ids, hot order, shards, cost model."""
     import legion_b200 as L
