@@ -227,6 +227,7 @@ def run_b200(args):
         r.run_batch(with_features=False, is_presc=True, stream=lp[step % NL])
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t_pre
+    r.set_dedup_capacity(max(1, r.max_ids()))     # hash dedup table: 2.5 x the largest presampled batch (no-op for the direct map)
     nh, _th = r.hotness()
     if world > 1:   # the path's one collective: NCCL all-reduce of the hotness histogram (replaces aggregate_access)
         cluster.allreduce_hotness(dist, nh, n=N, device=dev)

@@ -91,6 +91,10 @@ typedef struct {
 
 int lgn_create(const lgn_config* cfg, lgn_ctx** out);
 int lgn_destroy(lgn_ctx* ctx);
+/* The per-batch dedup table is allocated for the worst case B*(1+f1+f1*f2+..).  After presampling the real
+ * number of unique ids per batch is known (lgn_max_ids); shrinking the table to ~2.5x that keeps it in L2.
+ * Overflow is reported through lgn_status (LGN_E_CAPACITY), never silent.  No-op for the direct-map layout. */
+int lgn_set_dedup_capacity(lgn_ctx* ctx, int64_t expected_unique);
 /* index of this GPU inside its NVLink clique, once the clique layout is known (PreSc's cache_agg_mode) */
 int lgn_set_part(lgn_ctx* ctx, int32_t part);
 /* B*(1+f1+f1*f2+...) : per-pipe id / edge buffer capacity (Server.cu:184-196). */

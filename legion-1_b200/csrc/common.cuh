@@ -100,6 +100,83 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint4 v, unsigned long lon
     asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+// ---- per-batch dedup structure ------------------------------------------------------------
+// Two interchangeable layouts behind one interface:
+//   direct  int32 map[N]: value < CAND final local index, CAND+slot candidate, EMPTY unused.  One probe per
+//           access, but N*4 bytes per lane: L2-resident only for small graphs.
+//   hash    open-addressing table of (key << 32 | value) words sized for the BATCH (2^bits entries, a few MB),
+//           so it stays in L2 whatever N is.  64-bit atomicMin keeps the smallest value of a key because the key
+//           occupies the high word.  A claim returns the entry's index ("handle"); later passes address the
+//           entry directly, without probing.
+constexpr unsigned long long EMPTY64 = ~0ull;
+
+struct Dedup {
+    int32_t* map;
+    unsigned long long* tab;
+    uint32_t bits;            // 0 = direct map
+};
+
+__device__ __forceinline__ unsigned long long ld_keep_u64(const unsigned long long* p, unsigned long long pol)
+{
+    unsigned long long r;
+    asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_keep_u64(unsigned long long* p, unsigned long long v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long cas_keep_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val,
+                                                            unsigned long long)
+{
+    return atomicCAS(p, cmp, val);   // ptxas rejects .L2::cache_hint on atom.cas; the ld/red that follow carry the policy
+}
+__device__ __forceinline__ void red_min_keep_u64(unsigned long long* p, unsigned long long v, unsigned long long pol)
+{
+    asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
+// lower the value stored for `key` to `val` (claim the node for slot `val - CAND`, or for seed index `val`);
+// returns the entry's handle, or -1 if the hash table is full (reported through BatchState::status)
+__device__ __forceinline__ int32_t dedup_claim(const Dedup& dd, int32_t key, int32_t val, unsigned long long keep)
+{
+    if (dd.bits == 0) { red_min_keep(&dd.map[key], val, keep); return key; }
+    const uint32_t mask = (1u << dd.bits) - 1u;
+    uint32_t h = (uint32_t)key;          // murmur3 finaliser: node ids are structured (hub scatter, strided seed lists),
+    h ^= h >> 16; h *= 0x85ebca6bu;      // a single multiplicative hash clusters badly on them
+    h ^= h >> 13; h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    h &= mask;
+    const unsigned long long mine = ((unsigned long long)(uint32_t)key << 32) | (uint32_t)val;
+    for (int probe = 0; probe < 1024; probe++) {
+        unsigned long long cur = ld_keep_u64(dd.tab + h, keep);
+        if (cur == EMPTY64) {
+            cur = cas_keep_u64(dd.tab + h, EMPTY64, mine, keep);
+            if (cur == EMPTY64) return (int32_t)h;
+        }
+        if ((uint32_t)(cur >> 32) == (uint32_t)key) {
+            if ((uint32_t)cur > (uint32_t)val) red_min_keep_u64(dd.tab + h, mine, keep);   // values only ever decrease
+            return (int32_t)h;
+        }
+        h = (h + 1u) & mask;
+    }
+    return -1;
+}
+__device__ __forceinline__ int32_t dedup_value(const Dedup& dd, int32_t handle, unsigned long long keep)
+{
+    return dd.bits == 0 ? ld_keep(&dd.map[handle], keep) : (int32_t)(uint32_t)ld_keep_u64(dd.tab + handle, keep);
+}
+__device__ __forceinline__ void dedup_publish(const Dedup& dd, int32_t handle, int32_t key, int32_t pos, unsigned long long keep)
+{
+    if (dd.bits == 0) st_keep(&dd.map[handle], pos, keep);
+    else st_keep_u64(dd.tab + handle, ((unsigned long long)(uint32_t)key << 32) | (uint32_t)pos, keep);
+}
+__device__ __forceinline__ void dedup_release(const Dedup& dd, int32_t handle, unsigned long long keep)
+{
+    if (dd.bits == 0) st_keep(&dd.map[handle], EMPTY, keep);
+    else st_keep_u64(dd.tab + handle, EMPTY64, keep);
+}
+
 // ---- thrust::minstd_rand compatibility (Kernels.cu:402-405) ----------------
 // state after discard(z) from seed 1 is 48271^z mod (2^31-1); the next draw is
 // 48271^(z+1).  Mersenne modulus => fold instead of divide.

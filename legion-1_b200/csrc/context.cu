@@ -140,6 +140,14 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     c->max_rows = cfg->max_feature_rows > 0 ? cfg->max_feature_rows : cap;
     c->n_lanes = cfg->n_lanes > 0 ? cfg->n_lanes : LGN_PIPELINE_DEPTH;
     CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    {   // dedup layout: a batch-sized hash table (L2-resident for any N) unless the direct map itself is small
+        const char* dm = getenv("LGN_DEDUP");
+        const bool small_map = (size_t)cfg->n_nodes * 4 <= ((size_t)8 << 20);
+        c->dedup_hash = dm ? (dm[0] == 'h') : !small_map;
+        uint32_t bits = 10;
+        while (((long long)1 << bits) < 2 * cap && bits < 30) bits++;
+        c->dedup_bits_max = bits;
+    }
     long long slots_total = 0;
     {
         long long cur2 = cfg->batch_size;
@@ -160,7 +168,17 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         CK(cudaMemset(pp.nc, 0, 64));
         CK(cudaMemset(pp.ec, 0, 64));
         if (cfg->feat_dim > 0) CK(cudaMalloc(&pp.features, (size_t)c->max_rows * cfg->feat_dim * sizeof(float)));
-        CK(cudaMalloc(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
+        if (c->dedup_hash) {
+            const size_t entries = (size_t)1 << c->dedup_bits_max;
+            CK(cudaMalloc(&pp.dedup_tab, entries * sizeof(unsigned long long)));
+            CK(cudaMemset(pp.dedup_tab, 0xFF, entries * sizeof(unsigned long long)));
+            CK(cudaMalloc(&pp.slot_h, (max_slots + 16) * sizeof(int32_t)));
+            CK(cudaMalloc(&pp.id_h, cap * sizeof(int32_t)));
+            pp.dedup.map = nullptr; pp.dedup.tab = pp.dedup_tab; pp.dedup.bits = c->dedup_bits_max;
+        } else {
+            CK(cudaMalloc(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
+            pp.dedup.map = pp.slot_map; pp.dedup.tab = nullptr; pp.dedup.bits = 0;
+        }
         CK(cudaMalloc(&pp.agg_src_ids, cap * sizeof(int32_t)));
         CK(cudaMalloc(&pp.agg_dst_ids, cap * sizeof(int32_t)));
         CK(cudaMalloc(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
@@ -170,8 +188,10 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         CK(cudaMalloc(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
         CK(cudaMalloc(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
-        int rc = fill_i32(pp.slot_map, lgn::EMPTY, cfg->n_nodes, 0);
-        if (rc) return rc;
+        if (!c->dedup_hash) {
+            int rc = fill_i32(pp.slot_map, lgn::EMPTY, cfg->n_nodes, 0);
+            if (rc) return rc;
+        }
         // gathers run at the lowest priority so the latency-bound sampling kernels get SM slots first
         CK(cudaStreamCreateWithPriority(&pp.gather_stream, cudaStreamNonBlocking, prio_lo));
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&pp.ev_hop[i], cudaEventDisableTiming));
@@ -212,7 +232,7 @@ int lgn_destroy(lgn_ctx* c)
         lgn::Pipe& pp = c->pipe[p];
         cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
         cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
-        cudaFree(pp.slot_map); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids); cudaFree(pp.slot_dst); cudaFree(pp.slot_val);
+        cudaFree(pp.slot_map); cudaFree(pp.dedup_tab); cudaFree(pp.slot_h); cudaFree(pp.id_h); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids); cudaFree(pp.slot_dst); cudaFree(pp.slot_val);
         cudaFree(pp.scan_status); cudaFree(pp.scan_ticket); cudaFree(pp.state); cudaFree(pp.seed_stage);
         if (pp.gather_stream) cudaStreamDestroy(pp.gather_stream);
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
@@ -227,6 +247,17 @@ int lgn_destroy(lgn_ctx* c)
 }
 
 int64_t lgn_capacity(const lgn_ctx* c) { return c ? c->capacity : 0; }
+
+int lgn_set_dedup_capacity(lgn_ctx* c, int64_t expected_unique)
+{
+    if (!c || expected_unique <= 0) return LGN_E_ARG;
+    if (!c->dedup_hash) return LGN_OK;
+    for (int i = 0; i < c->n_lanes; i++) if (c->pipe[i].pending) CK(cudaEventSynchronize(c->pipe[i].ev_done));   // tables are empty between batches
+    uint32_t bits = 10;
+    while (((long long)1 << bits) < (5 * expected_unique) / 2 && bits < c->dedup_bits_max) bits++;
+    for (int i = 0; i < c->n_lanes; i++) c->pipe[i].dedup.bits = bits;
+    return LGN_OK;
+}
 
 int lgn_set_part(lgn_ctx* c, int32_t part)
 {

@@ -40,7 +40,11 @@ struct Pipe {
     int32_t* nc;
     int32_t* ec;
     // lane-private scratch
-    int32_t* slot_map;         // int32[N]
+    Dedup dedup;               // direct int32[N] map or batch-sized hash table (common.cuh)
+    unsigned long long* dedup_tab;   // hash allocation (2^dedup_bits_max entries)
+    int32_t* slot_map;         // direct allocation, int32[N]
+    int32_t* slot_h;           // int32[max slots of a hop]: hash handles of the draws
+    int32_t* id_h;             // int32[capacity]: hash handle of every id of the batch
     int32_t* agg_src_ids;      // raw ids, int32[capacity]
     int32_t* agg_dst_ids;
     int32_t* slot_dst;         // int32[sum of slots over hops]: draw results, then winners' local indices
@@ -75,6 +79,8 @@ struct lgn_ctx {
     int32_t seed_count[3];
     lgn::TopoView topo;
     lgn::FeatView feat;
+    int dedup_hash;            // 1: hash-table dedup, 0: direct map
+    uint32_t dedup_bits_max;   // log2 of the allocated hash table
     int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row
     int gather_ctas_per_sm;
     int shared_gather_stream;  // 1: all slots' gathers run back to back on one stream (one saturates HBM already)

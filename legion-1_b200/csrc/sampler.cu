@@ -34,14 +34,12 @@ constexpr int RESOLVE_THREADS = 256;
 constexpr int RESOLVE_VEC = 8;       // slots per thread, two int4 loads
 constexpr int RESOLVE_TILE = RESOLVE_THREADS * RESOLVE_VEC;
 
-constexpr unsigned long long FLAG_A = 1ull << 62, FLAG_P = 2ull << 62, FLAG_MASK = 3ull << 62;
-constexpr unsigned long long FIELD = 0x7fffffffull;
 
 // ------------------------------------------------------------------ batch begin
 __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__ src_ids,
                                                      const int32_t* __restrict__ src_labels, int32_t count,
                                                      int32_t* __restrict__ ids, int32_t* __restrict__ labels,
-                                                     int32_t* __restrict__ slot_map, long long n_nodes,
+                                                     const Dedup dd, int32_t* __restrict__ id_h, long long n_nodes,
                                                      int32_t* __restrict__ nc, int32_t* __restrict__ ec,
                                                      BatchState* __restrict__ st, uint32_t step)
 {
@@ -53,7 +51,12 @@ __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__
         ids[i] = id;
         labels[i] = src_labels ? src_labels[i] : -1;
         // Kernels.cu:88-92; duplicate seeds: lowest index wins (the reference races)
-        if (id >= 0 && id < n_nodes) red_min_keep(&slot_map[id], i, keep);
+        int32_t h = -1;
+        if (id >= 0 && id < n_nodes) {
+            h = dedup_claim(dd, id, i, keep);
+            if (h < 0) st->status = LGN_E_CAPACITY;
+        }
+        if (dd.bits) id_h[i] = h;
     }
     if (gtid < 16) {   // update_counter(op 0), Kernels.cu:118-127
         nc[gtid] = (gtid == 0 || gtid == 2 || gtid == 4) ? count : 0;
@@ -70,9 +73,9 @@ __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__
 template <int RNG, bool PRESC>
 __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant__ TopoView tv, const int32_t* __restrict__ ids,
                                                            const int32_t* __restrict__ agg_src_ids,
-                                                           int32_t* __restrict__ slot_dst,
-                                                           int32_t* __restrict__ slot_map,
-                                                           const BatchState* __restrict__ st, int hop, int f,
+                                                           int32_t* __restrict__ slot_dst, int32_t* __restrict__ slot_h,
+                                                           const Dedup dd,
+                                                           BatchState* __restrict__ st, int hop, int f,
                                                            unsigned long long seed, uint32_t* __restrict__ topo_hot,
                                                            long long n_nodes)
 {
@@ -158,13 +161,16 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
             const int s = s0 + u * SAMPLE_THREADS;
             if (s < total) {
                 int32_t d = dst[u];
+                int32_t h = -1;
                 if (d >= 0 && d < n_nodes) {                                   // Kernels.cu:411
-                    red_min_keep(&slot_map[d], CAND + (int32_t)(slot0 + s), keep);
-                    if (PRESC) atomicAdd(&s_cnt[il[u]], 1);
+                    h = dedup_claim(dd, d, CAND + (int32_t)(slot0 + s), keep);
+                    if (h < 0) { st->status = LGN_E_CAPACITY; d = -1; }
+                    else if (PRESC) atomicAdd(&s_cnt[il[u]], 1);
                 } else {
                     d = -1;
                 }
                 slot_dst[slot0 + s] = d;
+                if (dd.bits) slot_h[slot0 + s] = h;
             }
         }
     }
@@ -211,9 +217,10 @@ __device__ __forceinline__ void load_slots(const int32_t* __restrict__ p, long l
 // slot_map value next to the draw so pass 2 needs no second random access, and one packed
 // (valid, new) count per tile -- the cross-tile prefix is then a plain parallel sum in pass 2
 // instead of a serial look-back chain.
-__global__ void __launch_bounds__(RESOLVE_THREADS) k_mark(const int32_t* __restrict__ slot_dst, int32_t* __restrict__ slot_val,
-                                                          const int32_t* __restrict__ slot_map, const BatchState* __restrict__ st,
-                                                          int hop, int f, unsigned long long* __restrict__ tile_cnt)
+__global__ void __launch_bounds__(RESOLVE_THREADS) k_mark(const int32_t* __restrict__ slot_dst, const int32_t* __restrict__ slot_h,
+                                                          int32_t* __restrict__ slot_val, const Dedup dd,
+                                                          const BatchState* __restrict__ st, int hop, int f,
+                                                          unsigned long long* __restrict__ tile_cnt)
 {
     __shared__ unsigned long long s_red[RESOLVE_THREADS / 32];
     constexpr int V = RESOLVE_VEC;
@@ -224,10 +231,11 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_mark(const int32_t* __restr
     const unsigned long long keep = policy_evict_last();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long base = tile * RESOLVE_TILE + t * V;
-        int32_t d[V], v[V];
+        int32_t d[V], v[V], hd[V];
         load_slots(slot_dst, base, total, d, -1);
+        if (dd.bits) load_slots(slot_h, base, total, hd, -1);
 #pragma unroll
-        for (int j = 0; j < V; j++) v[j] = d[j] >= 0 ? ld_keep(&slot_map[d[j]], keep) : EMPTY;
+        for (int j = 0; j < V; j++) v[j] = d[j] >= 0 ? dedup_value(dd, dd.bits ? hd[j] : d[j], keep) : EMPTY;
         unsigned long long cnt = 0;
 #pragma unroll
         for (int j = 0; j < V; j++) cnt += (d[j] >= 0 ? 1ull : 0ull) + ((d[j] >= 0 && v[j] == CAND + (int32_t)(base + j)) ? (1ull << 32) : 0ull);
@@ -247,9 +255,10 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_mark(const int32_t* __restr
 // pass 2: compact the valid edges, append the winners to sampled_ids, write both local COO
 // indices; the last tile advances the counters (the reference's <<<1,1>>> update_counter).
 __global__ void __launch_bounds__(RESOLVE_THREADS) k_assign(
-    int32_t* __restrict__ slot_dst, const int32_t* __restrict__ slot_val, const int32_t* __restrict__ slot_dst_prev,
+    int32_t* __restrict__ slot_dst, const int32_t* __restrict__ slot_val, const int32_t* __restrict__ slot_h,
+    const int32_t* __restrict__ slot_dst_prev,
     int32_t* __restrict__ ids, int32_t* __restrict__ agg_src_ids, int32_t* __restrict__ agg_dst_ids,
-    int32_t* __restrict__ agg_src_off, int32_t* __restrict__ agg_dst_off, int32_t* __restrict__ slot_map,
+    int32_t* __restrict__ agg_src_off, int32_t* __restrict__ agg_dst_off, const Dedup dd, int32_t* __restrict__ id_h,
     int32_t* __restrict__ nc, int32_t* __restrict__ ec, BatchState* __restrict__ st, int hop, int f,
     const unsigned long long* __restrict__ tile_cnt, long long capacity)
 {
@@ -271,9 +280,10 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_assign(
         const unsigned long long prefix = block_sum_u64(part, s_red);
 
         const long long base = tile * RESOLVE_TILE + t * V;
-        int32_t d[V], v[V];
+        int32_t d[V], v[V], hd[V];
         load_slots(slot_dst, base, total, d, -1);
         load_slots(slot_val, base, total, v, EMPTY);
+        if (dd.bits) load_slots(slot_h, base, total, hd, -1);
         bool isnew[V];
         uint32_t cnt = 0;   // valid count | new count << 16
 #pragma unroll
@@ -309,13 +319,16 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_assign(
             const int32_t src = frontier[item];
             // local index of the frontier node: a seed's index sits in slot_map, a later hop's
             // item is the previous hop's edge, already relabelled (construct_graph, Kernels.cu:458-461)
-            int32_t dst_off = hop == 0 ? ld_keep(&slot_map[src], keep) : agg_src_off[hs.item_base + item];
+            int32_t dst_off = hop == 0 ? dedup_value(dd, dd.bits ? id_h[item] : src, keep) : agg_src_off[hs.item_base + item];
             if (dst_off < 0) dst_off = slot_dst_prev[-2 - dst_off];   // duplicate of the previous hop: its winner's entry
             int32_t src_off;
             if (isnew[j]) {                       // Kernels.cu:418-438
                 const long long pos = n_base + n_loc;
                 s_new[n_loc++] = d[j];
-                if (pos < capacity) st_keep(&slot_map[d[j]], (int32_t)pos, keep);
+                if (pos < capacity) {
+                    dedup_publish(dd, dd.bits ? hd[j] : d[j], d[j], (int32_t)pos, keep);
+                    if (dd.bits) id_h[pos] = hd[j];
+                }
                 slot_dst[base + j] = (int32_t)pos;   // winners publish their local index in their own slot
                 src_off = (int32_t)pos;
             } else {
@@ -363,11 +376,11 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k_assign(
 struct SlotRegions { long long off[LGN_MAX_HOPS + 1]; };
 
 template <bool PRESC>
-__global__ void __launch_bounds__(256) k_batch_end(const int32_t* __restrict__ ids, int32_t* __restrict__ slot_map,
+__global__ void __launch_bounds__(256) k_batch_end(const int32_t* __restrict__ ids, const Dedup dd, const int32_t* __restrict__ id_h,
                                                    BatchState* __restrict__ st, int n_hops,
                                                    uint32_t* __restrict__ node_hot, long long n_nodes,
                                                    int32_t* __restrict__ agg_src_off, const int32_t* __restrict__ slot_dst,
-                                                   const SlotRegions reg)
+                                                   const __grid_constant__ SlotRegions reg)
 {
     // patch the in-hop duplicates left by k_resolve (construct_graph's second lookup, Kernels.cu:458)
     const int n_edges = st->hop[n_hops].edge_base;
@@ -385,7 +398,8 @@ __global__ void __launch_bounds__(256) k_batch_end(const int32_t* __restrict__ i
         const int32_t id = ids[i];
         if (id >= 0 && id < n_nodes) {
             if (PRESC) atomicAdd(&node_hot[id], 1u);   // HotnessMeasure: ids of a batch are unique -> no contention
-            st_keep(&slot_map[id], EMPTY, keep);        // ClearPosMap + the reference's per-batch N/8-byte memset
+            const int32_t h = dd.bits ? id_h[i] : id;
+            if (h >= 0) dedup_release(dd, h, keep);     // ClearPosMap + the reference's per-batch N/8-byte memset
         }
     }
     if (PRESC && blockIdx.x == 0 && threadIdx.x == 0 && total > st->max_ids) st->max_ids = total;
@@ -401,7 +415,7 @@ void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const in
     int blocks = cdiv(count, 256);
     if (blocks < 1) blocks = 1;
     k_batch_begin<<<blocks, 256, 0, s>>>(ids + src_off, labels ? labels + src_off : nullptr, count, p.ids, p.labels,
-                                         p.slot_map, c->cfg.n_nodes, p.nc, p.ec, p.state, step);
+                                         p.dedup, p.id_h, c->cfg.n_nodes, p.nc, p.ec, p.state, step);
 }
 
 void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc)
@@ -415,16 +429,16 @@ void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc)
     int32_t* slot_dst = p.slot_dst + c->slot_off[hop];
     const int32_t* slot_prev = hop > 0 ? p.slot_dst + c->slot_off[hop - 1] : p.slot_dst;
 #define LGN_SAMPLE(R, P)                                                                                     \
-    k_sample<R, P><<<sblocks, SAMPLE_THREADS, 0, s>>>(c->topo, p.ids, p.agg_src_ids, slot_dst, p.slot_map, p.state, \
+    k_sample<R, P><<<sblocks, SAMPLE_THREADS, 0, s>>>(c->topo, p.ids, p.agg_src_ids, slot_dst, p.slot_h, p.dedup, p.state, \
                                                       hop, f, c->cfg.rng_seed, c->topo_hotness, c->cfg.n_nodes)
     if (c->cfg.rng_mode == LGN_RNG_MINSTD) { if (presc) LGN_SAMPLE(LGN_RNG_MINSTD, true); else LGN_SAMPLE(LGN_RNG_MINSTD, false); }
     else { if (presc) LGN_SAMPLE(LGN_RNG_PHILOX, true); else LGN_SAMPLE(LGN_RNG_PHILOX, false); }
 #undef LGN_SAMPLE
     int rblocks = cdiv(fmax * f, RESOLVE_TILE) + 1;
     if (rblocks > c->n_sm * c->resolve_ctas_per_sm) rblocks = c->n_sm * c->resolve_ctas_per_sm;
-    k_mark<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_val, p.slot_map, p.state, hop, f, p.scan_status);
-    k_assign<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_val, slot_prev, p.ids, p.agg_src_ids, p.agg_dst_ids,
-                                                 p.agg_src_off, p.agg_dst_off, p.slot_map, p.nc, p.ec, p.state, hop, f,
+    k_mark<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_h, p.slot_val, p.dedup, p.state, hop, f, p.scan_status);
+    k_assign<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_val, p.slot_h, slot_prev, p.ids, p.agg_src_ids, p.agg_dst_ids,
+                                                 p.agg_src_off, p.agg_dst_off, p.dedup, p.id_h, p.nc, p.ec, p.state, hop, f,
                                                  p.scan_status, c->capacity);
 }
 
@@ -435,8 +449,8 @@ void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc)
     if (blocks > c->n_sm * c->end_ctas_per_sm) blocks = c->n_sm * c->end_ctas_per_sm;
     SlotRegions reg;
     for (int h = 0; h <= LGN_MAX_HOPS; h++) reg.off[h] = c->slot_off[h];
-    if (presc) k_batch_end<true><<<blocks, 256, 0, s>>>(p.ids, p.slot_map, p.state, c->cfg.n_hops, c->node_hotness, c->cfg.n_nodes, p.agg_src_off, p.slot_dst, reg);
-    else k_batch_end<false><<<blocks, 256, 0, s>>>(p.ids, p.slot_map, p.state, c->cfg.n_hops, nullptr, c->cfg.n_nodes, p.agg_src_off, p.slot_dst, reg);
+    if (presc) k_batch_end<true><<<blocks, 256, 0, s>>>(p.ids, p.dedup, p.id_h, p.state, c->cfg.n_hops, c->node_hotness, c->cfg.n_nodes, p.agg_src_off, p.slot_dst, reg);
+    else k_batch_end<false><<<blocks, 256, 0, s>>>(p.ids, p.dedup, p.id_h, p.state, c->cfg.n_hops, nullptr, c->cfg.n_nodes, p.agg_src_off, p.slot_dst, reg);
 }
 
 }  // namespace lgn

@@ -96,6 +96,9 @@ class Runner:
         """GPURunner::RunOnce / RunPreSc minus the IPC handshake (Server.cu:284-328)."""
         check(lib().lgn_run_batch(self.handle, _vp(stream), int(with_features), int(is_presc)), "lgn_run_batch")
 
+    def set_dedup_capacity(self, expected_unique):
+        check(lib().lgn_set_dedup_capacity(self.handle, C.c_int64(expected_unique)), "lgn_set_dedup_capacity")
+
     def select_pipe(self, pipe):
         self.pipe = pipe
         check(lib().lgn_select_pipe(self.handle, pipe), "lgn_select_pipe")

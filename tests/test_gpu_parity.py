@@ -36,11 +36,13 @@ def _make_runner(L, d, batch, fanout, rng_mode, seed=7, feat=True, **kw):
     return r
 
 
+@pytest.mark.parametrize("dedup", ["hash", "direct"])
 @pytest.mark.parametrize("rng", ["minstd", "philox"])
 @pytest.mark.parametrize("fanout", [[25, 10], [15, 10, 5], [3], [40, 2]])
-def test_sampling_bit_exact(c1, rng, fanout):
+def test_sampling_bit_exact(c1, rng, fanout, dedup, monkeypatch):
     import legion_b200 as L
     from oracle import oracle as O
+    monkeypatch.setenv("LGN_DEDUP", dedup)     # batch-sized hash table vs direct int32[N] map: same bytes out
     mode = L.RNG_MINSTD if rng == "minstd" else L.RNG_PHILOX
     B = 1024
     r = _make_runner(L, c1, B, fanout, mode, feat=False)
@@ -59,10 +61,12 @@ def test_sampling_bit_exact(c1, rng, fanout):
     r.close()
 
 
-def test_sampling_edge_cases(small):
+@pytest.mark.parametrize("dedup", ["hash", "direct"])
+def test_sampling_edge_cases(small, dedup, monkeypatch):
     """ragged / empty / padded / duplicate seeds, zero-degree nodes."""
     import legion_b200 as L
     from oracle import oracle as O
+    monkeypatch.setenv("LGN_DEDUP", dedup)
     d = small
     # make some isolated nodes and a hub so deg==0, deg<f, deg>f all occur
     indptr, indices = d.indptr.copy(), d.indices.copy()
@@ -341,6 +345,31 @@ def test_run_batch_overlap_equals_stepwise_and_pipes(c1):
     b1_dag = r.fetch()
     for k in INT_KEYS + ("features", "labels"):
         assert np.array_equal(b1[k], b1_dag[k]), k
+    r.close()
+
+
+def test_hash_dedup_shrunk_table_and_overflow(c1, monkeypatch):
+    """the hash table sized from presampling (2.5 x max unique ids) gives the same bytes; a table that is too
+    small reports LGN_E_CAPACITY instead of corrupting the batch silently."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    monkeypatch.setenv("LGN_DEDUP", "hash")
+    d, fanout, B = c1, [25, 10], 1024
+    r = _make_runner(L, d, B, fanout, L.RNG_PHILOX, feat=False)
+    smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=7)
+    seeds = d.train_ids[:B]
+    want = _oracle_batch(O, smp, seeds, 0)
+    r.set_dedup_capacity(int(want["nc"][0]))
+    for step in range(2):
+        r.batch_from_host(seeds, None, step=0, pipe=step)
+        r.run_batch(with_features=False)
+        _assert_same(r.fetch(with_features=False), want)
+    assert r.status() == 0
+    r.set_dedup_capacity(64)                       # far too small for ~20k unique ids
+    r.batch_from_host(seeds, None, step=0, pipe=0)
+    r.run_batch(with_features=False)
+    r.read_counters()
+    assert r.status() == L._lib.E_CAPACITY
     r.close()
 
 
