@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+SHAPE_NAME = {"C1": "100K-node", "C2": "ogbn-products", "C3": "ogbn-papers100M", "C4": "UK-Union", "C5": "Friendster"}
 METRIC = "sampled edges/s"
 UNIT = "edges/s"
 
@@ -172,7 +173,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
             "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * t_time / k, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
-            "config": {"workload": f"{args.config} ogbn-products-shaped synthetic, batch {cfg['batch']}, fanout {cfg['fanout']}, "
+            "config": {"workload": f"{args.config} {SHAPE_NAME.get(args.config, 'synthetic')}-shaped synthetic, batch {cfg['batch']}, fanout {cfg['fanout']}, "
                                    f"{cfg['dim']}-d, CPU sampling+gather (oracle port of the reference path)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"{k} steps x 1 batch of {cfg['batch']} seeds"},
@@ -461,7 +462,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
-            "config": {"workload": f"{args.config} ogbn-products-shaped synthetic ({N} nodes, {ds.n_edges} edges, {D}-d), "
+            "config": {"workload": f"{args.config} {SHAPE_NAME.get(args.config, 'synthetic')}-shaped synthetic ({N} nodes, {ds.n_edges} edges, {D}-d), "
                                    f"GraphSAGE fanout {fanout}, batch {B}/GPU, rng {args.rng}, cache_frac {args.cache_frac}, kg {kg}, placement {args.placement} ({n_repl} rows replicated), {NL} batches in flight",
                        "parallelism": f"dp{world}: seeds tid%{world}, feature cache {args.placement} over {kg} GPU(s)",
                        "l2": "working set (feature shard %.2f GB + 9.8 MB slot table + 0.26 GB CSR) larger than the 126 MB L2; "
