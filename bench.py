@@ -248,7 +248,12 @@ def run_b200(args):
         cap = max(1, n_repl)
     else:
         cap = n_repl + cluster.capacity_for(n_cached - n_repl, kg)
-    slot_of = L.place_hybrid(order, cap, kg, n_repl, rank)
+    if kg > 1 and n_repl >= n_cached:      # nothing is partitioned: every GPU holds the whole cached set, no peer shards to bind
+        kg_bind, part_bind = 1, 0
+    else:
+        kg_bind, part_bind = kg, rank
+    r.set_part(part_bind)
+    slot_of = L.place_hybrid(order, cap, kg_bind, n_repl, part_bind)
     base = ds.features
     host_tier = None
     if args.cache_frac < 1.0 or (args.placement == "replicated" and n_repl < N):   # misses: pinned host memory over UVA
@@ -256,10 +261,10 @@ def run_b200(args):
         torch.from_numpy(host_tier.array).copy_(ds.features.cpu())
         base = host_tier
     r.bind_features(base)
-    my_shard = L.fill_feature_shard_hybrid(order, cap, kg, rank, n_repl, ds.features, D)
+    my_shard = L.fill_feature_shard_hybrid(order, cap, kg_bind, part_bind, n_repl, ds.features, D)
     shards = [my_shard]
     imported = []
-    if world > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
+    if kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
         import ctypes as C
         h = (C.c_uint8 * 64)()
         L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(my_shard.ptr), h), "ipc_export")
@@ -442,7 +447,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "r01b_gather_traffic.json")
     if os.path.exists(tp) and gather_calls:      # DRAM bytes per launch from the committed ncu --set full capture, scaled by rows
         traffic = json.load(open(tp))["traffic_bytes_per_row"] * rows / gather_calls
-    kname = "k_gather_bulk (cp.async.bulk feature extraction)" if os.environ.get("LGN_GATHER", "bulk")[0] != "l" else "k_gather_v4 (128-bit LDG feature extraction)"
+    kname = "k_gather_bulk (cp.async.bulk feature extraction)" if os.environ.get("LGN_GATHER", "bulk" if kg_bind == 1 else "ldg")[0] != "l" else "k_gather_v4 (128-bit LDG feature extraction)"
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, gather_calls),

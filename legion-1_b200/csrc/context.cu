@@ -206,11 +206,15 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     }
     {
         const char* gm = getenv("LGN_GATHER");
-        c->gather_mode = (gm && gm[0] == 'l') ? 0 : 1;
+        c->gather_mode = !gm ? -1 : (gm[0] == 'l' ? 0 : 1);   // -1 = auto (by tier mix)
         const char* gc = getenv("LGN_GATHER_CTAS");
         c->gather_ctas_per_sm = gc ? atoi(gc) : 1;
         if (c->gather_ctas_per_sm < 1) c->gather_ctas_per_sm = 1;
         auto knob = [](const char* name, int dflt) { const char* v = getenv(name); int x = v ? atoi(v) : dflt; return x < 1 ? 1 : x; };
+        c->gather_ldg_ctas = getenv("LGN_GATHER_LDG_CTAS") ? knob("LGN_GATHER_LDG_CTAS", 8) : 0;   // 0 = auto
+        c->gather_threads = knob("LGN_GATHER_THREADS", 256);
+        if (c->gather_threads > 256) c->gather_threads = 256;
+        c->gather_threads = (c->gather_threads + 31) / 32 * 32;
         c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
         c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);

@@ -81,8 +81,10 @@ struct lgn_ctx {
     lgn::FeatView feat;
     int dedup_hash;            // 1: hash-table dedup, 0: direct map
     uint32_t dedup_bits_max;   // log2 of the allocated hash table
-    int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row
+    int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row, -1 = auto
     int gather_ctas_per_sm;
+    int gather_ldg_ctas;       // CTAs per SM of the LDG gather
+    int gather_threads;        // rows in flight per CTA of the bulk-copy gather (<= 256)
     int shared_gather_stream;  // 1: all slots' gathers run back to back on one stream (one saturates HBM already)
     int sample_ctas_per_sm, resolve_ctas_per_sm, end_ctas_per_sm;   // grid caps (CTAs per SM) of the persistent kernels
     int n_sm;

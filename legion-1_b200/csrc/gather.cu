@@ -238,12 +238,15 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
     const int seg_slot = 3 + 2 * segment;
     bool vec = (dim & 3) == 0 && ((uintptr_t)c->feat.base & 15) == 0 && ((uintptr_t)p.features & 15) == 0;
     for (int i = 0; i < c->feat.n_parts; i++) vec = vec && ((uintptr_t)c->feat.shard_tab[i] & 15) == 0;
-    const int blocks = c->n_sm * 8;   // 2048 threads / SM, grid-stride over 32-row chunks
+    const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 8));   // grid-stride over 32-row chunks; < 8 CTAs/SM leaves room for the sampler
     FeatView fv = c->feat;
     const int nvec = dim >> 2;
-    if (vec && c->gather_mode == 1) {
+    // auto: rows of peer shards cross NVLink with ~3 us latency -> the register-staged LDG variant with a
+    // smaller grid measured faster there; all-local caches use the bulk-copy (TMA) variant
+    const int mode = c->gather_mode >= 0 ? c->gather_mode : (c->feat.n_parts > 1 ? 0 : 1);
+    if (vec && mode == 1) {
         // staging rows + one mbarrier per thread; keep <= ~100 KB per CTA so two CTAs (or the sampler) fit beside it
-        int threads = GATHER_THREADS;
+        int threads = c->gather_threads;
         while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
         const size_t smem = (size_t)threads * (dim * 4 + 8);
         static bool attr_set = false;

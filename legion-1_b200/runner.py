@@ -96,6 +96,9 @@ class Runner:
         """GPURunner::RunOnce / RunPreSc minus the IPC handshake (Server.cu:284-328)."""
         check(lib().lgn_run_batch(self.handle, _vp(stream), int(with_features), int(is_presc)), "lgn_run_batch")
 
+    def set_part(self, part):
+        check(lib().lgn_set_part(self.handle, C.c_int32(part)), "lgn_set_part")
+
     def set_dedup_capacity(self, expected_unique):
         check(lib().lgn_set_dedup_capacity(self.handle, C.c_int64(expected_unique)), "lgn_set_dedup_capacity")
 
