@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--placement", default="hybrid", choices=["sharded", "hybrid", "replicated"],
                     help="feature cache over the N GPUs: reference round-robin partition | hot rows replicated + rest partitioned | all replicated")
     ap.add_argument("--gpu-cache-gb", type=float, default=38.0, help="per-GPU feature-cache budget (legion_server.py default 38 GB)")
+    ap.add_argument("--no-train-epoch", action="store_true", help="skip the GraphSAGE epoch-time leg")
     ap.add_argument("--probe", action="store_true", help="debug: time sampling-only and gather-only loops")
     ap.add_argument("--lanes", type=int, default=4, help="mini-batches in flight per GPU (batch slots)")
     return ap.parse_args()
@@ -180,6 +181,73 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extra": {"feature_extract_GBps": float(np.mean(gbs))}}
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------
+# GraphSAGE epoch time (third part of the BASELINE metric): the reference trainer's structure
+# (legion_graphsage.py:36-89) fed by the pipeline, one process per GPU, DDP over NCCL
+# ------------------------------------------------------------------------------------------
+def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train_steps, epochs=2):
+    import torch
+    from legion_b200 import trainer
+
+    class _V:
+        def __init__(s, ptr, shape, ts):
+            s.__cuda_array_interface__ = {"shape": shape, "typestr": ts, "data": (int(ptr), False), "version": 2}
+
+    views = []
+    for q in range(NL):          # zero-copy tensors over the lane's output buffers (what ipc_service.get_next hands out)
+        v = r.view(q)
+        cap, rows = int(v.capacity), int(v.max_rows)
+        views.append(dict(feat=torch.as_tensor(_V(v.features, (rows, D), "<f4"), device=dev),
+                          lab=torch.as_tensor(_V(v.labels, (B,), "<i4"), device=dev),
+                          src=torch.as_tensor(_V(v.agg_src, (cap,), "<i4"), device=dev),
+                          dst=torch.as_tensor(_V(v.agg_dst, (cap,), "<i4"), device=dev)))
+    torch.manual_seed(0)
+    model = trainer.SAGE(D, 256, n_class, n_hops, dropout=0.5).to(dev)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+    opt = torch.optim.Adam(model.parameters(), lr=0.003)
+    model.train()
+    done_ev = [None] * NL
+    times, first, last = [], None, None
+    for ep in range(epochs):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(train_steps + NL - 1):
+            if i < train_steps:
+                q = i % NL
+                if done_ev[q] is not None:
+                    done_ev[q].synchronize()          # the trainer has finished reading this slot (ipc_service.synchronize())
+                r.batch_generate(L.MODE_TRAIN, B, i, stream=lp[q], pipe=q)
+                r.run_batch(with_features=True, stream=lp[q])
+            j = i - (NL - 1)
+            if j >= 0:
+                q = j % NL
+                nc, ec = r.read_counters(stream=lp[q], pipe=q)     # get_next(): waits for the slot, reads the counter blocks
+                V = views[q]
+                coo, sizes = [], []
+                for layer in range(n_hops):
+                    h = n_hops - 1 - layer
+                    e = int(ec[3 + h])
+                    coo.append((V["src"][:e], V["dst"][:e]))
+                    sizes.append((int(nc[7 + 2 * h]), int(nc[5 + 2 * h])))
+                total = sizes[0][0] if sizes else int(nc[4])
+                loss = trainer.train_step(model, opt, V["feat"][:total], V["lab"][:int(nc[4])], coo, sizes)
+                done_ev[q] = torch.cuda.Event()
+                done_ev[q].record()
+                if first is None:
+                    first = float(loss)
+                last = loss
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times.append(time.perf_counter() - t0)
+    return {"graphsage_epoch_s": times[-1], "graphsage_first_epoch_s": times[0], "graphsage_steps_per_epoch": train_steps,
+            "graphsage_model": f"{n_hops}-layer SAGEConv(mean) hidden 256, Adam, fp32, {'DDP' if world > 1 else 'single GPU'}",
+            "graphsage_loss_first": first, "graphsage_loss_last": float(last)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -484,6 +552,12 @@ def run_b200(args):
                       "presampling_epoch_s": t_pre, "tier_rows": tiers,
                       "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unprofiled": host_enqueue_plain_ms,
                       "ms_per_step_unprofiled": ms_plain / K}}
+
+    if not args.no_train_epoch:
+        try:
+            line["extra"].update(graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, cfg["n_class"], len(fanout), train_steps))
+        except Exception as e:      # noqa: BLE001  (the model leg must never invalidate the data-path numbers)
+            line["extra"]["graphsage_epoch_error"] = repr(e)[:200]
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
