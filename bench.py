@@ -497,6 +497,24 @@ def run_b200(args):
     row_bytes = 4 * D
     feat_gbps = job_rows * row_bytes / (ms_total / 1e3) / 1e9
 
+    # ---- the dominant kernel timed ALONE (no other batch in flight): K batches are sampled first, then only their
+    # feature-extraction launches are replayed back to back on one stream between CUDA events
+    alone_ms = alone_calls = alone_rows = 0
+    for i in range(W, W + min(K, 16)):
+        q = i % NL
+        r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[q], pipe=q)
+        r.run_batch(with_features=False, stream=lp[q])
+        nc_, _ = r.read_counters(stream=lp[q], pipe=q)
+        barrier()
+        r.select_pipe(q)
+        r.profile_enable(8)
+        for seg in range(len(fanout) + 1):
+            r.gather_segment(seg, stream=lp[q])
+        torch.cuda.synchronize()
+        ms_k, calls_k = r.profile_collect()
+        r.profile_enable(0)
+        alone_ms += ms_k[2]; alone_calls += calls_k[2]; alone_rows += int(nc_[0])
+
     # ---- roofline of the dominant kernel (feature gather), timed live with CUDA events ----
     hbm_peak, peak_src = peaks()
     ms_kind, calls = prof
@@ -519,6 +537,10 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, gather_calls),
+                "alone": {"achieved": alone_rows * (2 * row_bytes + 8) / (alone_ms / 1e3) / 1e9 if alone_ms else None,
+                          "frac": alone_rows * (2 * row_bytes + 8) / (alone_ms / 1e3) / 1e9 / hbm_peak if alone_ms else None,
+                          "launches": int(alone_calls), "avg_launch_us": 1e3 * alone_ms / max(1, alone_calls),
+                          "note": "same kernel, same rows, replayed with nothing else in flight (one launch per hop segment)"},
                 "note": "per-launch duration from CUDA events inside the timed region; %d batches are in flight, so launches of "
                         "different batches overlap each other and the sampling kernels and share HBM (alone and cold the hop-2 "
                         "launch runs at 0.65-0.8 of peak, profiles/README.md)" % NL,
