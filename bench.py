@@ -151,6 +151,51 @@ def cpu_leg(ds, cfg, seconds, steps_cap, rng_mode, seed, first_step=0):
     return edges / dt, rows * ds.dim * 4 / dt / 1e9, done, cores, dt
 
 
+def reference_gpu_leg(ds, cfg, n_batches=20):
+    """The reference's OWN kernels (Kernels.cu, GPUCache.cu, ... compiled unmodified for sm_100a into oracle/_ref by
+    oracle/ref_harness) driven through its own operator sequence on this GPU: presampling epoch, CandidateSelection /
+    CostModel / FillUp, then n steady-state batches.  Informational: 'the kernel to beat' of BASELINE.md section 3."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_legion.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libref_legion.so not built"}
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return {"unavailable": "no CUDA device"}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": repr(e)[:100]}
+    lib = C.CDLL(so)
+    lib.ref_create.restype = C.c_void_p
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    B, (f1, f2) = cfg["batch"], cfg["fanout"][:2]
+    train = np.ascontiguousarray(ds.train_ids, np.int32)
+    labels = np.ascontiguousarray(ds.labels[train], np.int32)
+    feat_bytes, topo_bytes = ds.n_nodes * ds.dim * 4, 8 * ds.n_nodes + 4 * ds.n_edges
+    cache_mem = int(1.02 * (feat_bytes + topo_bytes))      # a budget at which the reference's cost model caches (nearly) everything
+    h = C.c_void_p(lib.ref_create(p(ds.indptr), p(ds.indices), C.c_int32(ds.n_nodes), C.c_int64(ds.n_edges), p(ds.features),
+                                  C.c_int32(ds.dim), p(train), p(labels), C.c_int32(len(train)), C.c_int32(B), C.c_int32(f1),
+                                  C.c_int32(f2), C.c_int64(cache_mem)))
+    steps = (len(train) - 1) // B
+    cap = B * (1 + f1 + f1 * f2)
+    ids, s_ids, d_ids = (np.zeros(cap, np.int32) for _ in range(3))
+    nc, ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
+    t0 = time.perf_counter()
+    for it in range(steps):
+        lib.ref_presample_batch(h, C.c_int32(it), p(ids), p(s_ids), p(d_ids), p(nc), p(ec))
+    t_pre = time.perf_counter() - t0
+    qf, qt = np.zeros(ds.n_nodes, np.int32), np.zeros(ds.n_nodes, np.int32)
+    ncap, ecap = C.c_int32(), C.c_int32()
+    lib.ref_plan(h, C.c_uint64(10**9), p(qf), p(qt), C.byref(ncap), C.byref(ecap), None, C.c_int64(0))
+    ms, edges, rows = C.c_double(), C.c_int64(), C.c_int64()
+    lib.ref_time_batches(h, C.c_int32(0), C.c_int32(4), C.byref(ms), C.byref(edges), C.byref(rows))          # warm-up
+    lib.ref_time_batches(h, C.c_int32(4), C.c_int32(n_batches), C.byref(ms), C.byref(edges), C.byref(rows))
+    return {"ms_per_step": ms.value / n_batches, "value": edges.value / (ms.value / 1e3), "unit": UNIT,
+            "feature_extract_GBps": rows.value * ds.dim * 4 / (ms.value / 1e3) / 1e9, "batches": n_batches,
+            "feature_rows_cached_per_gpu": ncap.value, "topology_nodes_cached_per_gpu": ecap.value, "presampling_epoch_s": t_pre,
+            "note": "reference kernels recompiled for sm_100a (sm_80 upstream), minstd stream, cache budget = 1.02 x (features + topology)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own semantics on the host cores (oracle port)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +225,10 @@ def run_reference(args):
                              "sample": f"{k} steps x 1 batch of {cfg['batch']} seeds"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extra": {"feature_extract_GBps": float(np.mean(gbs))}}
+    try:
+        line["reference_gpu"] = reference_gpu_leg(ds, cfg)
+    except Exception as e:      # noqa: BLE001
+        line["reference_gpu"] = {"unavailable": repr(e)[:200]}
     emit(line)
 
 

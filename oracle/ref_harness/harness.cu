@@ -190,3 +190,38 @@ extern "C" void ref_train_batch(RefCtx* c, int32_t iter, int32_t* ids, int32_t* 
 }
 
 extern "C" int64_t ref_capacity(RefCtx* c) { return c->num_ids; }
+
+// Throughput of the reference's own steady-state loop (GPURunner::RunOnce minus the IPC handshake) on this
+// GPU: n batches starting at `first_iter`, wall-clock around the whole loop (the reference's operators block
+// the host several times per batch anyway, Kernels.cu:605-611, GPUCache.cu:394-395).
+#include <chrono>
+extern "C" void ref_time_batches(RefCtx* c, int32_t first_iter, int32_t n, double* ms_total, int64_t* edges, int64_t* rows)
+{
+    *edges = 0; *rows = 0;
+    cudaDeviceSynchronize();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++) {
+        const int iter = first_iter + i;
+        c->pool->SetCurrentMode(0);
+        c->pool->SetIter(iter % (c->train_step > 0 ? c->train_step : 1));
+        batch_generator_kernel(c->stream, c->node, c->cache, c->pool, c->batch, iter % (c->train_step > 0 ? c->train_step : 1), 0, 0, 0);
+        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 1, true);
+        GPU_Random_Sampling(c->stream, c->graph, c->cache, c->pool, c->f1, 2, false);
+        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 3, true);
+        GPU_Random_Sampling(c->stream, c->graph, c->cache, c->pool, c->f2, 4, false);
+        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 5, true);
+        make_update_plan(c->stream, c->graph, c->cache, c->pool, 0, 0);
+        cudaStreamSynchronize(c->stream);          // Server.cu:318-323 busy-polls the last event before the next batch
+        c->pipe ^= 1;
+        c->pool->SetCurrentPipe(c->pipe);
+    }
+    cudaDeviceSynchronize();
+    *ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int p = 0; p < 2; p++) {   // the last two batches' counters stand in for the per-batch work
+        int32_t nc[16], ec[16];
+        cudaMemcpy(nc, c->nc[p], 64, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ec, c->ec[p], 64, cudaMemcpyDeviceToHost);
+        *edges += ec[4]; *rows += nc[9];
+    }
+    *edges = *edges * n / 2; *rows = *rows * n / 2;
+}
