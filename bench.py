@@ -172,28 +172,38 @@ def reference_gpu_leg(ds, cfg, n_batches=20):
     train = np.ascontiguousarray(ds.train_ids, np.int32)
     labels = np.ascontiguousarray(ds.labels[train], np.int32)
     feat_bytes, topo_bytes = ds.n_nodes * ds.dim * 4, 8 * ds.n_nodes + 4 * ds.n_edges
-    cache_mem = int(1.02 * (feat_bytes + topo_bytes))      # a budget at which the reference's cost model caches (nearly) everything
-    h = C.c_void_p(lib.ref_create(p(ds.indptr), p(ds.indices), C.c_int32(ds.n_nodes), C.c_int64(ds.n_edges), p(ds.features),
-                                  C.c_int32(ds.dim), p(train), p(labels), C.c_int32(len(train)), C.c_int32(B), C.c_int32(f1),
-                                  C.c_int32(f2), C.c_int64(cache_mem)))
     steps = (len(train) - 1) // B
     cap = B * (1 + f1 + f1 * f2)
-    ids, s_ids, d_ids = (np.zeros(cap, np.int32) for _ in range(3))
-    nc, ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
-    t0 = time.perf_counter()
-    for it in range(steps):
-        lib.ref_presample_batch(h, C.c_int32(it), p(ids), p(s_ids), p(d_ids), p(nc), p(ec))
-    t_pre = time.perf_counter() - t0
-    qf, qt = np.zeros(ds.n_nodes, np.int32), np.zeros(ds.n_nodes, np.int32)
-    ncap, ecap = C.c_int32(), C.c_int32()
-    lib.ref_plan(h, C.c_uint64(10**9), p(qf), p(qt), C.byref(ncap), C.byref(ecap), None, C.c_int64(0))
-    ms, edges, rows = C.c_double(), C.c_int64(), C.c_int64()
-    lib.ref_time_batches(h, C.c_int32(0), C.c_int32(4), C.byref(ms), C.byref(edges), C.byref(rows))          # warm-up
-    lib.ref_time_batches(h, C.c_int32(4), C.c_int32(n_batches), C.byref(ms), C.byref(edges), C.byref(rows))
-    return {"ms_per_step": ms.value / n_batches, "value": edges.value / (ms.value / 1e3), "unit": UNIT,
-            "feature_extract_GBps": rows.value * ds.dim * 4 / (ms.value / 1e3) / 1e9, "batches": n_batches,
-            "feature_rows_cached_per_gpu": ncap.value, "topology_nodes_cached_per_gpu": ecap.value, "presampling_epoch_s": t_pre,
-            "note": "reference kernels recompiled for sm_100a (sm_80 upstream), minstd stream, cache budget = 1.02 x (features + topology)"}
+    best = None
+    # The reference's CostModel zeroes a tier's gain once that tier fits completely (GPUCache.cu:744-751), so with a
+    # generous budget it caches only ONE of the two tiers.  Sweep budgets and keep its fastest configuration.
+    for budget in (0.85 * feat_bytes, 0.95 * feat_bytes, 1.0 * feat_bytes + 0.5 * topo_bytes, 1.02 * (feat_bytes + topo_bytes)):
+        h = C.c_void_p(lib.ref_create(p(ds.indptr), p(ds.indices), C.c_int32(ds.n_nodes), C.c_int64(ds.n_edges), p(ds.features),
+                                      C.c_int32(ds.dim), p(train), p(labels), C.c_int32(len(train)), C.c_int32(B), C.c_int32(f1),
+                                      C.c_int32(f2), C.c_int64(int(budget))))
+        ids, s_ids, d_ids = (np.zeros(cap, np.int32) for _ in range(3))
+        nc, ec = np.zeros(16, np.int32), np.zeros(16, np.int32)
+        trans = 0
+        t0 = time.perf_counter()
+        for it in range(steps):
+            lib.ref_presample_batch(h, C.c_int32(it), p(ids), p(s_ids), p(d_ids), p(nc), p(ec))
+            trans += int(nc[4]) + int(ec[3]) + int(ec[4])      # one UVA read transaction per indptr pair and per neighbour id
+        t_pre = time.perf_counter() - t0
+        qf, qt = np.zeros(ds.n_nodes, np.int32), np.zeros(ds.n_nodes, np.int32)
+        ncap, ecap = C.c_int32(), C.c_int32()
+        lib.ref_plan(h, C.c_uint64(trans), p(qf), p(qt), C.byref(ncap), C.byref(ecap), None, C.c_int64(0))
+        ms, edges, rows = C.c_double(), C.c_int64(), C.c_int64()
+        lib.ref_time_batches(h, C.c_int32(0), C.c_int32(4), C.byref(ms), C.byref(edges), C.byref(rows))          # warm-up
+        lib.ref_time_batches(h, C.c_int32(4), C.c_int32(n_batches), C.byref(ms), C.byref(edges), C.byref(rows))
+        res = {"ms_per_step": ms.value / n_batches, "value": edges.value / (ms.value / 1e3), "unit": UNIT,
+               "feature_extract_GBps": rows.value * ds.dim * 4 / (ms.value / 1e3) / 1e9, "batches": n_batches,
+               "cache_budget_bytes": int(budget), "feature_rows_cached": ncap.value, "topology_nodes_cached": ecap.value,
+               "presampling_epoch_s": t_pre}
+        if best is None or res["ms_per_step"] < best["ms_per_step"]:
+            best = res
+    best["note"] = ("reference kernels recompiled unmodified for sm_100a (upstream targets sm_80), its own operator sequence and cache "
+                    "planner, minstd stream; fastest of 4 cache budgets (its cost model caches a single tier once everything fits)")
+    return best
 
 
 def run_reference(args):
