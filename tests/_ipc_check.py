@@ -30,11 +30,26 @@ def consume_and_check(dev, parts, n_nodes, avg_deg, dim, n_class, B, epochs, fan
     smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_MINSTD if rng == "minstd" else O.RNG_PHILOX, rng_seed=seed)
     for g in range(st.max_step):
         mode, local = O.mode_of_step(st, epochs, g), O.local_batch_id(st, epochs, g)
-        ids, feats, labels, b1s, b1d, b2s, b2d = ipc_service.get_next(d.dim)
-        sizes = ipc_service.get_block_size()
         seeds, slab = O.batch_generate(lists[mode][0], lists[mode][1].astype(np.int32), mode_batch[mode], local)
         want = smp.sample(seeds, step=local)
         nc, ec = want["nc"], want["ec"]
+        if len(fanout) != 2:        # additive k-hop consumer API (the reference's get_next is hard-wired to two hops)
+            H = len(fanout)
+            ids, feats, labels, blocks = ipc_service.get_next_k(d.dim, H)
+            sizes = ipc_service.get_block_sizes_k(H)
+            total = int(nc[7 + 2 * (H - 1)])
+            assert np.array_equal(ids.cpu().numpy(), want["sampled_ids"][:total]) and np.array_equal(labels.cpu().numpy(), slab)
+            assert np.array_equal(feats.cpu().numpy().view(np.uint32), d.features[want["sampled_ids"][:total]].view(np.uint32))
+            for layer, ((bs, bd), (n_src, n_dst)) in enumerate(zip(blocks, sizes)):
+                h = H - 1 - layer
+                e = int(ec[3 + h])
+                assert (n_src, n_dst) == (nc[7 + 2 * h], nc[5 + 2 * h])
+                assert np.array_equal(bs.cpu().numpy(), want["agg_src_off"][:e]) and np.array_equal(bd.cpu().numpy(), want["agg_dst_off"][:e])
+                assert e == 0 or (int(bs.max()) < n_src and int(bd.max()) < n_dst)      # dst nodes are a prefix of src nodes
+            ipc_service.synchronize()
+            continue
+        ids, feats, labels, b1s, b1d, b2s, b2d = ipc_service.get_next(d.dim)
+        sizes = ipc_service.get_block_size()
         assert sizes == [nc[9], nc[7], nc[7], nc[5]], (g, sizes, nc)
         assert np.array_equal(ids.cpu().numpy(), want["sampled_ids"][:nc[9]]), g
         assert np.array_equal(labels.cpu().numpy(), slab), g

@@ -31,8 +31,9 @@ def _start_server(workdir, ngpu, agg_mode, env):
     raise RuntimeError("server did not become ready:\n" + open(os.path.join(workdir, "server.log")).read()[-3000:])
 
 
-@pytest.mark.parametrize("rng,cache_mem,runner", [("minstd", 800_000, "fast"), ("philox", 10**9, "fast"), ("philox", 800_000, "ops")])
-def test_server_to_trainer_roundtrip(tmp_path, rng, cache_mem, runner):
+@pytest.mark.parametrize("rng,cache_mem,runner,fanout", [("minstd", 800_000, "fast", [25, 10]), ("philox", 10**9, "fast", [25, 10]),
+                                                         ("philox", 800_000, "ops", [25, 10]), ("philox", 800_000, "fast", [15, 10, 5])])
+def test_server_to_trainer_roundtrip(tmp_path, rng, cache_mem, runner, fanout):
     import legion_b200 as L
     from legion_b200 import dataset_io
     sys.path.insert(0, os.path.dirname(__file__))
@@ -45,9 +46,10 @@ def test_server_to_trainer_roundtrip(tmp_path, rng, cache_mem, runner):
     data_dir, work = str(tmp_path / "data"), str(tmp_path)
     dataset_io.write_dataset(data_dir, d)
     dataset_io.write_meta_config(work, data_dir, d, B, cache_mem, epochs)
-    srv = _start_server(work, 1, 0, {"LEGION_RNG": rng, "LEGION_SEED": "77", "LEGION_RUNNER": runner})
+    srv = _start_server(work, 1, 0, {"LEGION_RNG": rng, "LEGION_SEED": "77", "LEGION_RUNNER": runner,
+                                     "LEGION_FANOUT": ",".join(map(str, fanout))})
     try:
-        n = consume_and_check(dev=0, parts=1, B=B, epochs=epochs, fanout=[25, 10], rng=rng, seed=77, **cfg)
+        n = consume_and_check(dev=0, parts=1, B=B, epochs=epochs, fanout=fanout, rng=rng, seed=77, **cfg)
         assert n > 10
         assert srv.wait(timeout=60) == 0
         log = open(os.path.join(work, "server.log")).read()
