@@ -131,6 +131,8 @@ int lgn_batch_from_host(lgn_ctx* ctx, void* stream, int32_t pipe, const int32_t*
 int lgn_sample_hop(lgn_ctx* ctx, void* stream, int32_t hop, int32_t is_presc);
 /* ops 1,3,5,..: get_feature_kernel (Kernels.cu:707-748) for segment = 0..n_hops. */
 int lgn_gather_segment(lgn_ctx* ctx, void* stream, int32_t segment);
+/* n_segments adjacent segments in one launch (lgn_run_batch fuses the seeds with hop 1's new nodes) */
+int lgn_gather_segments(lgn_ctx* ctx, void* stream, int32_t first_segment, int32_t n_segments);
 /* op 6/7: make_update_plan / update_cache (Kernels.cu:759-805): node hotness when
  * is_presc (HotnessMeasure, GPUCache.cu:227-235) and scratch reset (ClearPosMap). */
 int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);

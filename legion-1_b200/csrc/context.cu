@@ -218,6 +218,15 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
         c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
+        const char* lp = getenv("LGN_L2_PERSIST");
+        c->l2_persist = lp ? atoi(lp) : 0;
+        if (c->l2_persist) {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, cfg->device));
+            size_t want = (size_t)c->n_lanes * (c->dedup_hash ? ((size_t)8 << c->dedup_bits_max) : (size_t)cfg->n_nodes * 4);
+            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        }
         const char* sg = getenv("LGN_SHARED_GATHER");
         c->shared_gather_stream = sg ? atoi(sg) : 0;
     }
@@ -310,6 +319,30 @@ int lgn_bind_feature_cache(lgn_ctx* c, int32_t n_parts, const float* const* shar
     return LGN_OK;
 }
 
+// ---------------------------------------------------------------- L2 persistence
+// The lane's dedup structure is touched at random several times per sampled edge while the gathers stream
+// hundreds of MB through L2: give it a persisting access-policy window on the lane's sampling stream
+// (hardware-managed set-aside, cudaLimitPersistingL2CacheSize) on top of the per-access evict_last hints.
+static int apply_l2_window(lgn_ctx* c, int pipe, cudaStream_t s)
+{
+    lgn::Pipe& pp = c->pipe[pipe];
+    if (!c->l2_persist || !s || pp.window_stream == s) return LGN_OK;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    size_t bytes = c->dedup_hash ? ((size_t)8 << pp.dedup.bits) : (size_t)c->cfg.n_nodes * 4;
+    int dev = c->cfg.device, max_win = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+    v.accessPolicyWindow.base_ptr = c->dedup_hash ? (void*)pp.dedup_tab : (void*)pp.slot_map;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v));
+    pp.window_stream = s;
+    return LGN_OK;
+}
+
 // ---------------------------------------------------------------- operator timing
 struct ProfScope {
     lgn_ctx* c; cudaStream_t s; int idx;
@@ -383,6 +416,7 @@ int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int
     const long long off = size * counter;
     c->cur_pipe = pipe;
     if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent((cudaStream_t)stream, c->pipe[pipe].ev_done, 0));   // slot reuse (WAR)
+    { int rcw = apply_l2_window(c, pipe, (cudaStream_t)stream); if (rcw) return rcw; }
     ProfScope prof(c, (cudaStream_t)stream, 0);
     launch_batch_begin(c, (cudaStream_t)stream, c->seed_ids[mode], c->seed_labels[mode], (int32_t)off, (int32_t)size, (uint32_t)counter);
     CK(cudaGetLastError());
@@ -396,6 +430,7 @@ int lgn_batch_from_host(lgn_ctx* c, void* stream, int32_t pipe, const int32_t* s
     cudaStream_t s = (cudaStream_t)stream;
     c->cur_pipe = pipe;
     if (c->pipe[pipe].pending) CK(cudaStreamWaitEvent(s, c->pipe[pipe].ev_done, 0));   // slot reuse (WAR)
+    { int rcw = apply_l2_window(c, pipe, s); if (rcw) return rcw; }
     int32_t* stage = c->pipe[pipe].seed_stage;
     if (count > 0) CK(cudaMemcpyAsync(stage, seeds, (size_t)count * 4, cudaMemcpyHostToDevice, s));
     if (count > 0 && labels) CK(cudaMemcpyAsync(stage + c->cfg.batch_size, labels, (size_t)count * 4, cudaMemcpyHostToDevice, s));
@@ -422,6 +457,16 @@ int lgn_gather_segment(lgn_ctx* c, void* stream, int32_t segment)
     if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
     ProfScope prof(c, (cudaStream_t)stream, 2);
     launch_gather(c, (cudaStream_t)stream, segment, 1);
+    CK(cudaGetLastError());
+    return LGN_OK;
+}
+
+int lgn_gather_segments(lgn_ctx* c, void* stream, int32_t first, int32_t n)
+{
+    if (!c || first < 0 || n < 1 || first + n > c->cfg.n_hops + 1) return LGN_E_ARG;
+    if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
+    ProfScope prof(c, (cudaStream_t)stream, 2);
+    launch_gather(c, (cudaStream_t)stream, first, n);
     CK(cudaGetLastError());
     return LGN_OK;
 }

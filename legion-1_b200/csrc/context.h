@@ -58,6 +58,7 @@ struct Pipe {
     cudaEvent_t ev_end;        // batch_end enqueued on the sampling stream
     cudaEvent_t ev_done;       // everything of the batch in this slot is complete
     bool pending;
+    cudaStream_t window_stream;   // sampling stream that already carries this lane's L2 access-policy window
 };
 
 }  // namespace lgn
@@ -79,6 +80,7 @@ struct lgn_ctx {
     int32_t seed_count[3];
     lgn::TopoView topo;
     lgn::FeatView feat;
+    int l2_persist;            // 1: dedup structures get a persisting L2 access-policy window on the sampling stream
     int dedup_hash;            // 1: hash-table dedup, 0: direct map
     uint32_t dedup_bits_max;   // log2 of the allocated hash table
     int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row, -1 = auto

@@ -88,6 +88,9 @@ class Runner:
         """Feature_Extractor::run (Operator.cu:58-78)."""
         check(lib().lgn_gather_segment(self.handle, _vp(stream), segment), "lgn_gather_segment")
 
+    def gather_segments(self, first, count, stream=None):
+        check(lib().lgn_gather_segments(self.handle, _vp(stream), first, count), "lgn_gather_segments")
+
     def finish_batch(self, is_presc=False, stream=None):
         """Cache_Planner::run + Cache_Updater::run (Operator.cu:80-123)."""
         check(lib().lgn_finish_batch(self.handle, _vp(stream), int(is_presc)), "lgn_finish_batch")
