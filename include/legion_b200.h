@@ -58,6 +58,10 @@ int lgn_copy_d2h(void* host_dst, const void* dev_src, int64_t bytes);
 int lgn_memset_d(void* dev_dst, int value, int64_t bytes);
 int lgn_copy_d2d(void* dev_dst, const void* dev_src, int64_t bytes);   /* any two devices (UVA) */
 int lgn_device_synchronize(void);
+/* streams for callers that do not link the CUDA runtime themselves (non-blocking; high_priority for sampling lanes) */
+int lgn_stream_create(void** stream, int32_t high_priority);
+int lgn_stream_destroy(void* stream);
+int lgn_stream_synchronize(void* stream);
 /* all-pairs cudaDeviceEnablePeerAccess among the first n devices
  * (GPUGraphStore::EnableP2PAccess, GPUGraphStore.cu:145-168). */
 int lgn_enable_peer_access(int32_t n_devices);

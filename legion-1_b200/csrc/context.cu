@@ -63,6 +63,19 @@ int lgn_memset_d(void* d, int v, int64_t bytes) { CK(cudaMemset(d, v, (size_t)by
 int lgn_copy_d2d(void* d, const void* s, int64_t bytes) { CK(cudaMemcpy(d, s, (size_t)bytes, cudaMemcpyDefault)); return LGN_OK; }
 int lgn_device_synchronize(void) { CK(cudaDeviceSynchronize()); return LGN_OK; }
 
+int lgn_stream_create(void** stream, int32_t high_priority)
+{
+    if (!stream) return LGN_E_ARG;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    *stream = (void*)s;
+    return LGN_OK;
+}
+int lgn_stream_destroy(void* stream) { CK(cudaStreamDestroy((cudaStream_t)stream)); return LGN_OK; }
+int lgn_stream_synchronize(void* stream) { CK(cudaStreamSynchronize((cudaStream_t)stream)); return LGN_OK; }
+
 int lgn_enable_peer_access(int32_t n)
 {
     int cur = 0;
@@ -102,6 +115,8 @@ int lgn_ipc_import(const uint8_t handle[64], void** p)
 int lgn_ipc_close(void* p) { CK(cudaIpcCloseMemHandle(p)); return LGN_OK; }
 
 // ---------------------------------------------------------------- context
+static void invalidate_graphs_impl(lgn_ctx* c);
+static inline void invalidate_graphs(lgn_ctx* c) { invalidate_graphs_impl(c); }
 static int fill_i32(int32_t* p, int32_t v, long long n, cudaStream_t s);
 
 __global__ void k_fill_i32(int32_t* p, int32_t v, long long n)
@@ -197,6 +212,7 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&pp.ev_hop[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.ev_end, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pp.ev_join, cudaEventDisableTiming));
     }
     if (cfg->enable_hotness) {                                                   // GPUCache.cu:256-261 (u64 there)
         CK(cudaMalloc(&c->node_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
@@ -218,6 +234,8 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
         c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
+        const char* ug = getenv("LGN_GRAPH");
+        c->use_graphs = ug ? atoi(ug) : 1;
         const char* lp = getenv("LGN_L2_PERSIST");
         c->l2_persist = lp ? atoi(lp) : 0;
         if (c->l2_persist) {
@@ -251,6 +269,8 @@ int lgn_destroy(lgn_ctx* c)
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
         if (pp.ev_end) cudaEventDestroy(pp.ev_end);
         if (pp.ev_done) cudaEventDestroy(pp.ev_done);
+        if (pp.ev_join) cudaEventDestroy(pp.ev_join);
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (pp.graph_exec[a][b]) cudaGraphExecDestroy(pp.graph_exec[a][b]);
     }
     cudaFree(c->node_hotness); cudaFree(c->topo_hotness);
     lgn_profile_enable(c, 0);
@@ -269,6 +289,7 @@ int lgn_set_dedup_capacity(lgn_ctx* c, int64_t expected_unique)
     uint32_t bits = 10;
     while (((long long)1 << bits) < (5 * expected_unique) / 2 && bits < c->dedup_bits_max) bits++;
     for (int i = 0; i < c->n_lanes; i++) c->pipe[i].dedup.bits = bits;
+    invalidate_graphs(c);
     return LGN_OK;
 }
 
@@ -277,10 +298,21 @@ int lgn_set_part(lgn_ctx* c, int32_t part)
     if (!c || part < 0 || part >= LGN_MAX_PARTS) return LGN_E_ARG;
     c->cfg.part = part;
     c->feat.my_part = part;
+    invalidate_graphs(c);
     return LGN_OK;
 }
 
 // ---------------------------------------------------------------- storage binding
+static void invalidate_graphs_impl(lgn_ctx* c)
+{
+    for (int p = 0; p < c->n_lanes; p++)
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) {
+                if (c->pipe[p].graph_exec[a][b]) { cudaGraphExecDestroy(c->pipe[p].graph_exec[a][b]); c->pipe[p].graph_exec[a][b] = nullptr; }
+                c->pipe[p].graph_calls[a][b] = 0;
+            }
+}
+
 int lgn_bind_seeds(lgn_ctx* c, int32_t mode, const int32_t* ids, const int32_t* labels, int32_t count)
 {
     if (!c || mode < 0 || mode > 2 || count < 0 || (count > 0 && !ids)) return LGN_E_ARG;
@@ -291,12 +323,14 @@ int lgn_bind_topology(lgn_ctx* c, const int64_t* indptr, const int32_t* indices)
 {
     if (!c || !indptr || !indices) return LGN_E_ARG;
     c->topo.base_indptr = indptr; c->topo.base_indices = indices;
+    invalidate_graphs(c);
     return LGN_OK;
 }
 int lgn_bind_topology_cache(lgn_ctx* c, int32_t n_parts, const int64_t* const* indptr_tab, const int32_t* const* indices_tab,
                             const int32_t* slot_of, int64_t cap)
 {
     if (!c || n_parts < 0 || n_parts > LGN_MAX_PARTS) return LGN_E_ARG;
+    invalidate_graphs(c);
     if (!slot_of || n_parts == 0) { c->topo.slot_of = nullptr; return LGN_OK; }
     if (cap <= 0 || !indptr_tab || !indices_tab) return LGN_E_ARG;
     for (int i = 0; i < n_parts; i++) { c->topo.indptr_tab[i] = indptr_tab[i]; c->topo.indices_tab[i] = indices_tab[i]; }
@@ -307,11 +341,13 @@ int lgn_bind_features(lgn_ctx* c, const float* features)
 {
     if (!c || !features) return LGN_E_ARG;
     c->feat.base = features;
+    invalidate_graphs(c);
     return LGN_OK;
 }
 int lgn_bind_feature_cache(lgn_ctx* c, int32_t n_parts, const float* const* shard_tab, const int32_t* slot_of, int64_t cap)
 {
     if (!c || n_parts < 0 || n_parts > LGN_MAX_PARTS) return LGN_E_ARG;
+    invalidate_graphs(c);
     if (!slot_of || n_parts == 0) { c->feat.slot_of = nullptr; c->feat.n_parts = 0; return LGN_OK; }
     if (cap <= 0 || !shard_tab) return LGN_E_ARG;
     for (int i = 0; i < n_parts; i++) c->feat.shard_tab[i] = shard_tab[i];
@@ -486,13 +522,10 @@ int lgn_finish_batch(lgn_ctx* c, void* stream, int32_t is_presc)
 // busy-polls the last event before touching the next batch, Server.cu:318-323) the caller's
 // stream is NOT joined here: the next batch's sampling overlaps this batch's gathers, the
 // slot's completion is the event lgn_wait_pipe / lgn_read_counters wait on.
-int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_presc)
+static int enqueue_batch(lgn_ctx* c, cudaStream_t s, bool feats, int32_t is_presc, bool join)
 {
-    if (!c) return LGN_E_ARG;
     lgn::Pipe& pp = c->pipe[c->cur_pipe];
-    cudaStream_t s = (cudaStream_t)stream, g = c->shared_gather_stream ? c->pipe[0].gather_stream : pp.gather_stream;
-    const bool feats = with_features && !is_presc && c->feat.base && c->cfg.feat_dim > 0;
-    if (with_features && !is_presc && !feats) return LGN_E_STATE;
+    cudaStream_t g = c->shared_gather_stream ? c->pipe[0].gather_stream : pp.gather_stream;
     int rc;
     // feature extraction of the seeds is fused with hop 1's segment (two small, latency-bound gathers
     // become one); with no hops at all the seeds are gathered alone
@@ -512,12 +545,51 @@ int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_pr
         }
     }
     if ((rc = lgn_finish_batch(c, s, is_presc))) return rc;
-    if (feats) {   // slot complete = last gather done AND batch end done
+    if (join) {          // captured form: the gather branch must rejoin the origin stream
+        if (feats) {
+            CK(cudaEventRecord(pp.ev_join, g));
+            CK(cudaStreamWaitEvent(s, pp.ev_join, 0));
+        }
+    } else if (feats) {   // slot complete = last gather done AND batch end done
         CK(cudaEventRecord(pp.ev_end, s));
         CK(cudaStreamWaitEvent(g, pp.ev_end, 0));
         CK(cudaEventRecord(pp.ev_done, g));
     } else {
         CK(cudaEventRecord(pp.ev_done, s));
+    }
+    return LGN_OK;
+}
+
+int lgn_run_batch(lgn_ctx* c, void* stream, int32_t with_features, int32_t is_presc)
+{
+    if (!c) return LGN_E_ARG;
+    lgn::Pipe& pp = c->pipe[c->cur_pipe];
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool feats = with_features && !is_presc && c->feat.base && c->cfg.feat_dim > 0;
+    if (with_features && !is_presc && !feats) return LGN_E_STATE;
+    const int fi = feats ? 1 : 0, pi = is_presc ? 1 : 0;
+    // CUDA graph replay: the per-batch DAG has no host-visible parameters (every count lives in device memory), so it
+    // is captured once per slot and replayed.  Needs a real stream (the legacy default stream cannot be captured),
+    // no operator timing, and one eager call first (lazy module loading / attribute setup are not capturable).
+    const bool graphable = c->use_graphs && s != nullptr && c->prof_cap == 0 && !c->shared_gather_stream;
+    if (graphable && pp.graph_calls[fi][pi] >= 1) {
+        if (!pp.graph_exec[fi][pi]) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_batch(c, s, feats, is_presc, true);
+            cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return lgn_cuda_fail(e, "cudaStreamEndCapture");
+            e = cudaGraphInstantiate(&pp.graph_exec[fi][pi], graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return lgn_cuda_fail(e, "cudaGraphInstantiate");
+        }
+        CK(cudaGraphLaunch(pp.graph_exec[fi][pi], s));
+        CK(cudaEventRecord(pp.ev_done, s));
+    } else {
+        int rc = enqueue_batch(c, s, feats, is_presc, false);
+        if (rc) return rc;
+        pp.graph_calls[fi][pi]++;
     }
     pp.pending = true;
     return LGN_OK;

@@ -58,6 +58,9 @@ struct Pipe {
     cudaEvent_t ev_end;        // batch_end enqueued on the sampling stream
     cudaEvent_t ev_done;       // everything of the batch in this slot is complete
     bool pending;
+    cudaGraphExec_t graph_exec[2][2];   // [with_features][is_presc]: the captured RunOnce / RunPreSc DAG of this slot
+    int graph_calls[2][2];
+    cudaEvent_t ev_join;                // joins the gather branch back into the captured stream
     cudaStream_t window_stream;   // sampling stream that already carries this lane's L2 access-policy window
 };
 
@@ -80,6 +83,7 @@ struct lgn_ctx {
     int32_t seed_count[3];
     lgn::TopoView topo;
     lgn::FeatView feat;
+    int use_graphs;            // 1: lgn_run_batch replays a captured CUDA graph per slot (one launch instead of ~20 API calls)
     int l2_persist;            // 1: dedup structures get a persisting L2 access-policy window on the sampling stream
     int dedup_hash;            // 1: hash-table dedup, 0: direct map
     uint32_t dedup_bits_max;   // log2 of the allocated hash table

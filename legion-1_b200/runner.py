@@ -13,6 +13,23 @@ from . import _lib
 from ._lib import DevArray, MappedHostArray, check, lib, _vp
 
 
+class Stream:
+    """a CUDA stream owned through the C-ABI (lgn_stream_create)."""
+
+    def __init__(self, high_priority=True):
+        h = C.c_void_p()
+        check(lib().lgn_stream_create(C.byref(h), int(high_priority)), "lgn_stream_create")
+        self.handle = h.value
+
+    def synchronize(self):
+        check(lib().lgn_stream_synchronize(C.c_void_p(self.handle)), "lgn_stream_synchronize")
+
+    def close(self):
+        if self.handle:
+            lib().lgn_stream_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+
 def _ptr(x):
     if isinstance(x, MappedHostArray):
         return C.c_void_p(x.ptr)

@@ -373,6 +373,48 @@ def test_hash_dedup_shrunk_table_and_overflow(c1, monkeypatch):
     r.close()
 
 
+def test_cuda_graph_replay_matches_eager(c1):
+    """on a real stream lgn_run_batch replays a captured CUDA graph from the second call on: same bytes as the
+    eager path and as the oracle, across lanes, after re-binding (graphs are invalidated) and with hotness."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    d, fanout, B = c1, [25, 10], 1024
+    r = _make_runner(L, d, B, fanout, L.RNG_PHILOX, n_lanes=3, enable_hotness=True)
+    streams = [L.Stream() for _ in range(3)]
+    smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=7)
+    smp.enable_hotness()
+    for step in range(9):                       # 3 calls per lane: eager, capture + replay, replay
+        q = step % 3
+        seeds = d.train_ids[step * B:(step + 1) * B]
+        presc = step >= 6
+        r.batch_from_host(seeds, d.labels[seeds], step=step, stream=streams[q].handle, pipe=q)
+        r.run_batch(with_features=not presc, is_presc=presc, stream=streams[q].handle)
+        got = r.fetch(with_features=not presc, stream=streams[q].handle)
+        smp.topo_hotness_enabled = presc
+        if presc:
+            want = _oracle_batch(O, smp, seeds, step)
+        else:
+            keep = (smp.topo_hotness, smp.node_hotness)
+            smp.topo_hotness = smp.node_hotness = None
+            want = _oracle_batch(O, smp, seeds, step)
+            smp.topo_hotness, smp.node_hotness = keep
+        _assert_same(got, want, ctx=f"step {step}: ")
+        if not presc:
+            assert np.array_equal(got["features"].view(np.uint32), d.features[want["sampled_ids"]].view(np.uint32))
+    nh, th = r.hotness()
+    assert np.array_equal(nh.numpy(), smp.node_hotness) and np.array_equal(th.numpy(), smp.topo_hotness)
+    r.bind_features(L.DevArray.from_numpy(d.features * 2.0))       # re-binding must not replay a stale graph
+    seeds = d.train_ids[:B]
+    r.batch_from_host(seeds, None, step=0, stream=streams[0].handle, pipe=0)
+    r.run_batch(with_features=True, stream=streams[0].handle)
+    got = r.fetch(stream=streams[0].handle)
+    assert np.array_equal(got["features"], d.features[got["sampled_ids"]] * 2.0)
+    assert r.status() == 0
+    r.close()
+    for s in streams:
+        s.close()
+
+
 def test_capacity_overflow_is_reported(small):
     """reference: silent overflow of the 1.2x feature buffer (Server.cu:275); here: status code."""
     import legion_b200 as L
