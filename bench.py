@@ -503,9 +503,15 @@ def run_b200(args):
                 step_resident(i)
         both(8); print(f"full pipeline, {NL} lanes: {ev_time(both, 40):.4f} ms/step", file=sys.stderr)
         if os.environ.get("LGN_NCU_RANGE"):       # ncu --replay-mode app-range: whole-range metrics under real concurrency
+            def samp4(n):
+                for i in range(n):
+                    r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % NL], pipe=i % NL)
+                    r.run_batch(with_features=False, stream=lp[i % NL])
+            fn = samp4 if os.environ["LGN_NCU_RANGE"] == "samp" else both
+            fn(8)
             barrier()
             torch.cuda.profiler.start()
-            both(40)
+            fn(40)
             barrier()
             torch.cuda.profiler.stop()
             return
