@@ -169,7 +169,7 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         for (int h = 0; h < cfg->n_hops; h++) { c->slot_off[h] = slots_total; cur2 *= cfg->fanout[h]; slots_total += (cur2 + 15) / 16 * 16; }
         for (int h = cfg->n_hops; h <= LGN_MAX_HOPS; h++) c->slot_off[h] = slots_total;
     }
-    const long long n_status = ((max_slots + 1023) / 1024 + 1) * LGN_MAX_HOPS;   // >= tiles of any RESOLVE_TILE >= 1024
+    const long long n_tiles = (max_slots + 1023) / 1024 + 1;   // >= tiles of any RESOLVE_TILE >= 1024
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int p = 0; p < c->n_lanes; p++) {      // CUDA_IPC_Service.cu:140-215, Server.cu:217-231
@@ -198,8 +198,7 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         CK(cudaMalloc(&pp.agg_dst_ids, cap * sizeof(int32_t)));
         CK(cudaMalloc(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
         CK(cudaMalloc(&pp.slot_val, (max_slots + 16) * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.scan_status, n_status * sizeof(unsigned long long)));
-        CK(cudaMalloc(&pp.scan_ticket, LGN_MAX_HOPS * sizeof(int32_t)));
+        CK(cudaMalloc(&pp.tile_cnt, n_tiles * sizeof(unsigned long long)));
         CK(cudaMalloc(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
         CK(cudaMalloc(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
@@ -264,7 +263,7 @@ int lgn_destroy(lgn_ctx* c)
         cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
         cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
         cudaFree(pp.slot_map); cudaFree(pp.dedup_tab); cudaFree(pp.slot_h); cudaFree(pp.id_h); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids); cudaFree(pp.slot_dst); cudaFree(pp.slot_val);
-        cudaFree(pp.scan_status); cudaFree(pp.scan_ticket); cudaFree(pp.state); cudaFree(pp.seed_stage);
+        cudaFree(pp.tile_cnt); cudaFree(pp.state); cudaFree(pp.seed_stage);
         if (pp.gather_stream) cudaStreamDestroy(pp.gather_stream);
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
         if (pp.ev_end) cudaEventDestroy(pp.ev_end);

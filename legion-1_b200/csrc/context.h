@@ -49,8 +49,7 @@ struct Pipe {
     int32_t* agg_dst_ids;
     int32_t* slot_dst;         // int32[sum of slots over hops]: draw results, then winners' local indices
     int32_t* slot_val;         // int32[max slots of a hop]: slot_map value probed by k_mark
-    unsigned long long* scan_status;   // decoupled look-back tile descriptors
-    int32_t* scan_ticket;      // int32[LGN_MAX_HOPS]
+    unsigned long long* tile_cnt;      // packed (valid, new) count per 2048-slot tile of the current hop
     BatchState* state;         // device
     int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
     cudaStream_t gather_stream;

@@ -436,10 +436,10 @@ void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc)
 #undef LGN_SAMPLE
     int rblocks = cdiv(fmax * f, RESOLVE_TILE) + 1;
     if (rblocks > c->n_sm * c->resolve_ctas_per_sm) rblocks = c->n_sm * c->resolve_ctas_per_sm;
-    k_mark<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_h, p.slot_val, p.dedup, p.state, hop, f, p.scan_status);
+    k_mark<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_h, p.slot_val, p.dedup, p.state, hop, f, p.tile_cnt);
     k_assign<<<rblocks, RESOLVE_THREADS, 0, s>>>(slot_dst, p.slot_val, p.slot_h, slot_prev, p.ids, p.agg_src_ids, p.agg_dst_ids,
                                                  p.agg_src_off, p.agg_dst_off, p.dedup, p.id_h, p.nc, p.ec, p.state, hop, f,
-                                                 p.scan_status, c->capacity);
+                                                 p.tile_cnt, c->capacity);
 }
 
 void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc)
