@@ -61,6 +61,38 @@ def test_server_to_trainer_roundtrip(tmp_path, rng, cache_mem, runner, fanout):
             srv.kill()
 
 
+def test_trainer_example_trains_through_ipc(tmp_path):
+    """the GraphSAGE example (reference trainer's structure, this repo's ipc_service + DGL stand-ins) consumes a
+    whole run of the server: train / valid / test phases, loss finite, accuracy printed, both sides exit cleanly."""
+    import legion_b200 as L
+    from legion_b200 import dataset_io, legion_server
+    cfg = dict(n_nodes=12_000, avg_deg=10.0, dim=24, n_class=5)
+    d = L.synth.make_dataset(cfg["n_nodes"], cfg["avg_deg"], cfg["dim"], n_class=cfg["n_class"])
+    data_dir, work = str(tmp_path / "data"), str(tmp_path)
+    dataset_io.write_dataset(data_dir, d)
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:      # the launcher writes ./meta_config exactly like the reference's legion_server.py
+        custom = ",".join(map(str, [data_dir, d.n_nodes, d.n_edges, d.dim, len(d.train_ids), len(d.valid_ids), len(d.test_ids)]))
+        assert legion_server.main(["--custom", custom, "--train_batch_size", "200", "--epoch", "2", "--cache_memory", "1000000000",
+                                   "--gpu_number", "1", "--dry_run"]) == 0
+    finally:
+        os.chdir(cwd)
+    assert open(os.path.join(work, "meta_config")).read().split()[1:5] == ["200", str(d.n_nodes), str(d.n_edges), str(d.dim)]
+    srv = _start_server(work, 1, 0, {"LEGION_RNG": "philox"})
+    try:
+        ex = os.path.join(ROOT, "examples", "train_graphsage.py")
+        out = subprocess.run([sys.executable, ex, "--gpu", "0", "--features_num", str(d.dim), "--class_num", "5", "--hidden_dim", "32",
+                              "--epoch", "2"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert out.stdout.count("Epoch:") == 2 and "Accuracy on test data" in out.stdout
+        assert "nan" not in out.stdout.lower()
+        assert srv.wait(timeout=60) == 0
+    finally:
+        if srv.poll() is None:
+            srv.kill()
+
+
 @pytest.mark.parametrize("cache_mem", [600_000, 10**9])
 def test_two_gpu_clique_server(tmp_path, cache_mem):
     """`legion 2 1`: one NVLink clique of two GPUs -- seeds partitioned tid % 2, hotness summed across the
