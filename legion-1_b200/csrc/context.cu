@@ -155,6 +155,8 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     c->max_rows = cfg->max_feature_rows > 0 ? cfg->max_feature_rows : cap;
     c->n_lanes = cfg->n_lanes > 0 ? cfg->n_lanes : LGN_PIPELINE_DEPTH;
     CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    lgn::gather_init_device();
+    CK(cudaGetLastError());
     {   // dedup layout: a batch-sized hash table (L2-resident for any N) unless the direct map itself is small
         const char* dm = getenv("LGN_DEDUP");
         const bool small_map = (size_t)cfg->n_nodes * 4 <= ((size_t)32 << 20);   // measured: direct wins at 9.8 MB (C2), hash at 444 MB (C3)

@@ -249,8 +249,6 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
         int threads = c->gather_threads;
         while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
         const size_t smem = (size_t)threads * (dim * 4 + 8);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     } else if (vec && nvec <= 32)
         k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
@@ -260,6 +258,12 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
         k_gather_v4<4><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else
         k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+}
+
+// per-device function attributes (a process may drive several GPUs): called once per context from lgn_create
+void gather_init_device()
+{
+    cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,

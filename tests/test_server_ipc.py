@@ -103,7 +103,7 @@ def test_two_gpu_clique_server(tmp_path, cache_mem):
     from legion_b200 import dataset_io
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    cfg = dict(n_nodes=12_000, avg_deg=10.0, dim=24, n_class=5)
+    cfg = dict(n_nodes=12_000, avg_deg=10.0, dim=128 if cache_mem > 10**8 else 24, n_class=5)   # 128-d rows need the >48 KB smem opt-in on BOTH devices
     d = L.synth.make_dataset(cfg["n_nodes"], cfg["avg_deg"], cfg["dim"], n_class=cfg["n_class"])
     B, epochs = 100, 2
     data_dir, work = str(tmp_path / "data"), str(tmp_path)
