@@ -323,10 +323,22 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # LGN_BENCH_BACKEND=gloo: diagnostic run without any NCCL communicator in the process (DESIGN.md section 4,
+        # NVLink tier); the GraphSAGE/DDP leg needs NCCL and is skipped then
+        if os.environ.get("LGN_BENCH_BACKEND", "nccl") == "gloo":
+            dist.init_process_group("gloo")
+            args.no_train_epoch = True
+        else:
+            dist.init_process_group("nccl", device_id=dev)
+    rdev = dev if world == 1 or dist.get_backend() == "nccl" else torch.device("cpu")     # where reduced scalars live
     cfg = workload(args)
     N, D, B, fanout = cfg["n_nodes"], cfg["dim"], cfg["batch"], cfg["fanout"]
     rng_mode = L.RNG_PHILOX if args.rng == "philox" else L.RNG_MINSTD
+    early_shard = None
+    if os.environ.get("LGN_BENCH_EARLY_SHARD") and world > 1 and args.placement == "sharded":
+        # experiment: reserve the feature shard before anything else is allocated on the device
+        from legion_b200 import cluster as _cl
+        early_shard = L.DevArray.zeros((_cl.capacity_for(int(N * args.cache_frac), world), D), np.float32)
 
     # ---- dataset, resident in HBM before the timed region --------------------------------
     dmin = L.synth.calibrate_dmin(cfg["avg_deg"], N)
@@ -358,7 +370,17 @@ def run_b200(args):
     r.set_dedup_capacity(max(1, r.max_ids()))     # hash dedup table: 2.5 x the largest presampled batch (no-op for the direct map)
     nh, _th = r.hotness()
     if world > 1:   # the path's one collective: NCCL all-reduce of the hotness histogram (replaces aggregate_access)
-        cluster.allreduce_hotness(dist, nh, n=N, device=dev)
+        how = os.environ.get("LGN_BENCH_HOTNESS", "nccl" if dist.get_backend() == "nccl" else "host")
+        nh_t = torch.as_tensor(cluster._DeviceView(nh.ptr, N), device=dev)
+        if how == "none":       # diagnostic: no reduction at all, identical (id-ordered) placement on every rank
+            nh_t.zero_()
+        elif how == "host":     # diagnostic: reduce through host memory (gloo needs CPU tensors)
+            h = nh_t.cpu()
+            grp = dist.new_group(backend="gloo") if dist.get_backend() == "nccl" else None
+            dist.all_reduce(h, group=grp)
+            nh_t.copy_(h)
+        else:
+            cluster.allreduce_hotness(dist, nh, n=N, device=dev)
         torch.cuda.synchronize()
     order = L.hot_order(nh)
     kg = world
@@ -388,7 +410,9 @@ def run_b200(args):
         torch.from_numpy(host_tier.array).copy_(ds.features.cpu())
         base = host_tier
     r.bind_features(base)
-    my_shard = L.fill_feature_shard_hybrid(order, cap, kg_bind, part_bind, n_repl, ds.features, D)
+    if early_shard is not None and early_shard.shape != (cap, D):
+        early_shard = None
+    my_shard = L.fill_feature_shard_hybrid(order, cap, kg_bind, part_bind, n_repl, ds.features, D, out=early_shard)
     shards = [my_shard]
     imported = []
     if kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
@@ -468,7 +492,7 @@ def run_b200(args):
             busy += (cur_b - cur_a) if cur_b is not None else 0.0
             prof = r.profile_collect() + (busy,)
             r.profile_enable(0)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms], device=rdev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), prof
@@ -563,7 +587,7 @@ def run_b200(args):
             hop_edges[h] += e_h; hop_new[h] += int(nc[6 + 2 * h])
             hop_edges_prev, prev_e = e_h, int(ec[3 + h])
     assert r.status(stream=sp) == 0, "device-side capacity overflow"
-    tot = torch.tensor([edges, rows], device=dev, dtype=torch.float64)
+    tot = torch.tensor([edges, rows], device=rdev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot)
     job_edges, job_rows = float(tot[0].item()), float(tot[1].item())

@@ -240,9 +240,9 @@ def place_hybrid(order, cap, kg, n_repl, my_part, stream=None):
     return slot_of
 
 
-def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features, dim, stream=None):
+def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features, dim, stream=None, out=None):
     n = order.shape[0]
-    shard = DevArray.zeros((cap, dim), np.float32)
+    shard = out if out is not None else DevArray.zeros((cap, dim), np.float32)
     check(lib().lgn_fill_feature_shard_hybrid(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int32(j), C.c_int64(n_repl),
                                               _ptr(features), C.c_int32(dim), _ptr(shard), _vp(stream)), "lgn_fill_feature_shard_hybrid")
     return shard
