@@ -8,6 +8,7 @@
 #include "Operator.h"
 #include "Server.h"
 
+#include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -21,6 +22,7 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../../include/legion_b200.h"
@@ -32,6 +34,12 @@
             fprintf(stderr, "legion_b200: %s failed: %s %s\n", what, lgn_error_string(rc_), lgn_last_cuda_error()); \
             exit(EXIT_FAILURE);   /* the reference exits on any CUDA error too (Kernels.cuh:14-22) */           \
         }                                                                                                       \
+    } while (0)
+
+#define CUDA_DIE(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) { fprintf(stderr, "legion_b200: %s: %s\n", #call, cudaGetErrorString(e_)); exit(EXIT_FAILURE); } \
     } while (0)
 
 namespace {
@@ -83,18 +91,27 @@ void read_file(const std::string& file, void* dst, size_t bytes, bool required =
     // parallel pread instead of the reference's single-threaded element-wise mmap copy loops
     const int nt = bytes > (64u << 20) ? 8 : 1;
     std::vector<std::thread> th;
+    std::vector<size_t> got(nt, 0);
     const size_t chunk = (bytes + nt - 1) / nt;
     for (int t = 0; t < nt; t++)
-        th.emplace_back([=]() {
+        th.emplace_back([=, &got]() {
             size_t off = t * chunk, end = off + chunk < bytes ? off + chunk : bytes;
             while (off < end) {
                 ssize_t r = pread(fd, (char*)dst + off, end - off, (off_t)off);
+                if (r < 0 && errno == EINTR) continue;
                 if (r <= 0) break;
                 off += (size_t)r;
+                got[t] += (size_t)r;
             }
         });
     for (auto& t : th) t.join();
     close(fd);
+    size_t total = 0;
+    for (size_t g : got) total += g;
+    if (total != bytes) {   // a truncated file would otherwise run with uninitialised topology / features
+        fprintf(stderr, "legion_b200: %s holds %zu bytes, meta_config implies %zu\n", file.c_str(), total, bytes);
+        exit(EXIT_FAILURE);
+    }
 }
 
 void load_dataset(Dataset& d, int parts)
@@ -106,6 +123,10 @@ void load_dataset(Dataset& d, int parts)
     std::getline(meta, line);
     std::istringstream iss(line);
     iss >> d.path >> d.batch >> d.n_nodes >> d.n_edges >> d.dim >> d.n_train >> d.n_valid >> d.n_test >> d.cache_memory >> d.epochs >> d.partition_flag;
+    if (iss.fail() || d.batch <= 0 || d.n_nodes <= 0 || d.n_edges < 0 || d.dim <= 0 || d.n_train < 0 || d.n_valid < 0 || d.n_test < 0 || d.epochs < 0) {
+        fprintf(stderr, "legion_b200: ./meta_config needs 11 fields: path batch nodes edges dim train valid test cache_bytes epochs partition\n");
+        exit(EXIT_FAILURE);
+    }
     std::cout << "Dataset path:       " << d.path << "\nRaw Batchsize:      " << d.batch << "\nGraph nodes num:    " << d.n_nodes
               << "\nGraph edges num:    " << d.n_edges << "\nFeature dim:        " << d.dim << "\nTraining set num:   " << d.n_train
               << "\nValidation set num: " << d.n_valid << "\nTesting set num:    " << d.n_test << "\nCache memory:       " << d.cache_memory
@@ -135,8 +156,9 @@ void load_dataset(Dataset& d, int parts)
         d.ids[m].assign(parts, {});
         d.lab[m].assign(parts, {});
         for (int32_t tid : raw[m]) {
+            if (tid < 0 || tid >= d.n_nodes) { fprintf(stderr, "legion_b200: %s holds node id %d outside [0, %d)\n", names[m], tid, d.n_nodes); exit(EXIT_FAILURE); }
             int p = (m == 0 && !part_of.empty()) ? part_of[tid] : tid % parts;               // GPUGraphStore.cu:332-376
-            if (p < parts) { d.ids[m][p].push_back(tid); d.lab[m][p].push_back(d.labels[tid]); }
+            if (p >= 0 && p < parts) { d.ids[m][p].push_back(tid); d.lab[m][p].push_back(d.labels[tid]); }
         }
     }
     std::cout << "Finish Reading All Files\n";
@@ -227,14 +249,14 @@ public:
     void Initialize(RunnerParams* params) override
     {
         dev_ = params->device_id;
-        cudaSetDevice(dev_);
+        CUDA_DIE(cudaSetDevice(dev_));
         env_ = (IPCEnv*)params->env;
         st_.ctx = (lgn_ctx*)params->cache;      // the per-GPU context built by the server
         st_.device = dev_;
         int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        cudaStreamCreateWithPriority(&streams_[0], cudaStreamNonBlocking, hi);
-        cudaStreamCreateWithPriority(&streams_[1], cudaStreamNonBlocking, hi);
+        CUDA_DIE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_DIE(cudaStreamCreateWithPriority(&streams_[0], cudaStreamNonBlocking, hi));
+        CUDA_DIE(cudaStreamCreateWithPriority(&streams_[1], cudaStreamNonBlocking, hi));
         const int hops = (int)params->fanout.size();
         op_num_ = (hops + 1) * 2 + 2;                                     // Server.cu:198-207
         ops_.resize(op_num_);
@@ -246,7 +268,7 @@ public:
         params_.resize(op_num_);
         events_.resize(op_num_);
         for (int i = 0; i < op_num_; i++) {
-            cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming);
+            CUDA_DIE(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
             params_[i] = OpParams{dev_, streams_[i % 2], events_[i], &st_, nullptr, nullptr, nullptr, env_, 0, false, params->in_memory};
         }
         for (int i = 0; i < hops; i++) params_[2 * i + 2].neighbor_count = params->fanout[i];
@@ -282,8 +304,8 @@ public:
                 params_[i].is_presc = false;
                 ops_[i]->run(&params_[i]);
             }
-            cudaStreamSynchronize(streams_[1]);
-            cudaStreamSynchronize(streams_[0]);
+            CUDA_DIE(cudaStreamSynchronize(streams_[1]));
+            CUDA_DIE(cudaStreamSynchronize(streams_[0]));
             LGN_DIE(lgn_ipc_server_post(env_->ipc, dev_, pipe_), "IPCPost");
         } else {
             LGN_DIE(lgn_batch_generate(st_.ctx, streams_[pipe_], pipe_, st_.mode, st_.batch_size, st_.iter), "lgn_batch_generate");
@@ -300,6 +322,13 @@ public:
     {
         Drain();
         LGN_DIE(lgn_ipc_server_wait(env_->ipc, dev_, (pipe_ + 1) % LGN_PIPELINE_DEPTH), "IPCWait(final)");   // Server.cu:330-334
+        cudaSetDevice(dev_);
+        for (Operator* op : ops_) delete op;
+        ops_.clear();
+        for (cudaEvent_t e : events_) cudaEventDestroy(e);
+        events_.clear();
+        cudaStreamDestroy(streams_[0]);
+        cudaStreamDestroy(streams_[1]);
     }
     RunnerState st_;
 
@@ -362,6 +391,7 @@ public:
                 LGN_DIE(lgn_device_alloc(&dl, (int64_t)cnt * 4), "alloc labels");
                 if (cnt) { LGN_DIE(lgn_copy_h2d(di, ds_.ids[m][i].data(), (int64_t)cnt * 4), "h2d ids"); LGN_DIE(lgn_copy_h2d(dl, ds_.lab[m][i].data(), (int64_t)cnt * 4), "h2d labels"); }
                 LGN_DIE(lgn_bind_seeds(ctx_[i], m, (int32_t*)di, (int32_t*)dl, (int32_t)cnt), "lgn_bind_seeds");
+                owned_.push_back({i, di}); owned_.push_back({i, dl});
             }
             LGN_DIE(lgn_bind_topology(ctx_[i], ds_.indptr_d, ds_.indices_d), "lgn_bind_topology");   // host CSR over UVA
             LGN_DIE(lgn_bind_features(ctx_[i], ds_.feat_d), "lgn_bind_features");
@@ -384,7 +414,11 @@ public:
                 runners_[i]->SyncAll();
             });
         for (auto& t : th) t.join();
-        const int kg = cache_agg_mode == 1 ? 2 : cache_agg_mode == 2 ? 4 : cache_agg_mode == 3 ? 8 : 1;   // GPUCache.cu:593-607
+        int kg = cache_agg_mode == 1 ? 2 : cache_agg_mode == 2 ? 4 : cache_agg_mode == 3 ? 8 : 1;   // GPUCache.cu:593-607
+        if (kg > n_) {   // the reference computes Kc = 0 here and serves without any cache
+            std::cout << "cache aggregate mode " << cache_agg_mode << " asks for " << kg << " GPUs per clique, only " << n_ << " present: using " << n_ << "\n";
+            kg = n_;
+        }
         const int kc = n_ / kg;
         std::cout << "NVLink Clique: " << kc << " GPU Per Clique: " << kg << std::endl;
         const int64_t N = ds_.n_nodes;
@@ -454,6 +488,7 @@ public:
                 LGN_DIE(lgn_fill_topo_shard((int32_t*)ot, N, ecap, kg, j, ds_.indptr_d, ds_.indices_d, (int64_t*)tip, (int32_t*)tix, &cnt, nullptr), "TopoFillUp");
                 LGN_DIE(lgn_device_synchronize(), "sync");
                 fshard[j] = (float*)shard; fslot[j] = (int32_t*)fs; tslot[j] = (int32_t*)ts; tptr[j] = (int64_t*)tip; tidx[j] = (int32_t*)tix;
+                for (void* q : {shard, fs, ts, tip, tix}) owned_.push_back({dev, q});
                 if (j > 0) { lgn_device_free(oq); lgn_device_free(ot); }
             }
             for (int j = 0; j < kg; j++) {   // every GPU of the clique sees all shards (P2P) and its own replica of the maps
@@ -486,6 +521,9 @@ public:
     {
         for (int i = 0; i < n_; i++) runners_[i]->Finalize(params_[i]);
         for (int i = 0; i < n_; i++) lgn_destroy(ctx_[i]);
+        for (auto& a : owned_) { lgn_set_device(a.first); lgn_device_free(a.second); }   // seed sets, cache shards, slot tables
+        owned_.clear();
+        for (int i = 0; i < n_; i++) { delete runners_[i]; delete params_[i]; }
         lgn_ipc_server_destroy(env_.ipc);
         lgn_host_free(ds_.indptr_h); lgn_host_free(ds_.indices_h); lgn_host_free(ds_.feat_h);
         std::cout << "Server Stopped\n";
@@ -499,5 +537,6 @@ private:
     std::vector<lgn_ctx*> ctx_;
     std::vector<GPURunner*> runners_;
     std::vector<RunnerParams*> params_;
+    std::vector<std::pair<int, void*>> owned_;   // (device, allocation) released in Finalize
 };
 Server* NewGPUServer() { return new GPUServer(); }

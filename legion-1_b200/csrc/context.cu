@@ -130,9 +130,12 @@ static int fill_i32(int32_t* p, int32_t v, long long n, cudaStream_t s)
     return LGN_OK;
 }
 
+static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long long max_slots);
+
 int lgn_create(const lgn_config* cfg, lgn_ctx** out)
 {
     if (!cfg || !out) return LGN_E_ARG;
+    *out = nullptr;
     if (cfg->n_nodes <= 0 || cfg->n_nodes > 0x7fffffffLL || cfg->feat_dim < 0 || cfg->batch_size <= 0) return LGN_E_ARG;
     if (cfg->n_hops < 0 || cfg->n_hops > LGN_MAX_HOPS || cfg->part < 0 || cfg->part >= LGN_MAX_PARTS) return LGN_E_ARG;
     if (cfg->rng_mode != LGN_RNG_MINSTD && cfg->rng_mode != LGN_RNG_PHILOX) return LGN_E_ARG;
@@ -147,8 +150,22 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     }
     CK(cudaSetDevice(cfg->device));
     lgn_ctx* c = new (std::nothrow) lgn_ctx();
-    if (!c) return LGN_E_ARG;
+    if (!c) return LGN_E_SYS;
     memset(c, 0, sizeof(*c));
+    const int rc = create_impl(c, cfg, cap, max_slots);
+    if (rc != LGN_OK) {          // release whatever was allocated before the failure; keep the CUDA error text
+        char keep[sizeof(g_lgn_cuda_err)];
+        memcpy(keep, g_lgn_cuda_err, sizeof(keep));
+        lgn_destroy(c);
+        memcpy(g_lgn_cuda_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = c;
+    return LGN_OK;
+}
+
+static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long long max_slots)
+{
     c->cfg = *cfg;
     c->capacity = cap;
     c->max_slots = max_slots;
@@ -251,7 +268,6 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
     }
     c->feat.my_part = cfg->part;
     CK(cudaDeviceSynchronize());
-    *out = c;
     return LGN_OK;
 }
 

@@ -134,8 +134,7 @@ int lgn_ipc_server_destroy(lgn_ipc_server* s)
             sem_name(name, sizeof(name), "sem_r_", d, p); sem_unlink(name);
             sem_name(name, sizeof(name), "sem_w_", d, p); sem_unlink(name);
         }
-    if (s->shm) munmap(s->shm, sizeof(ShmLayout));
-    if (s->fd > 0) close(s->fd);
+    if (s->shm) { munmap(s->shm, sizeof(ShmLayout)); close(s->fd); }
     shm_unlink(kShmName);
     delete s;
     return LGN_OK;
@@ -150,7 +149,8 @@ int lgn_ipc_client_open(int32_t device, lgn_ipc_client** out)
     c->dev = device;
     int rc = map_shm(false, &c->fd, &c->shm);
     if (rc) { delete c; return rc; }
-    CK(cudaSetDevice(device));
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) { lgn_ipc_client_close(c); return lgn_cuda_fail(ce, "cudaSetDevice"); }
     char name[64];
     for (int p = 0; p < LGN_PIPELINE_DEPTH; p++) {                                // ipc_cuda_kernel.cu:62-92
         for (int k = 0; k < MEMORY_USAGE; k++) {
@@ -158,13 +158,14 @@ int lgn_ipc_client_open(int32_t device, lgn_ipc_client** out)
             memcpy(&h, (void*)&c->shm->mem[device][p][k], sizeof(h));
             static const cudaIpcMemHandle_t zero = {};
             if (memcmp(&h, &zero, sizeof(h)) == 0) continue;   // not published (yet)
-            CK(cudaIpcOpenMemHandle(&c->ptr[p][k], h, cudaIpcMemLazyEnablePeerAccess));
+            ce = cudaIpcOpenMemHandle(&c->ptr[p][k], h, cudaIpcMemLazyEnablePeerAccess);
+            if (ce != cudaSuccess) { c->ptr[p][k] = nullptr; lgn_ipc_client_close(c); return lgn_cuda_fail(ce, "cudaIpcOpenMemHandle"); }
         }
         sem_name(name, sizeof(name), "sem_r_", device, p);
         c->semr[p] = sem_open(name, O_CREAT | O_RDWR, 0666, 0);
         sem_name(name, sizeof(name), "sem_w_", device, p);
         c->semw[p] = sem_open(name, O_CREAT | O_RDWR, 0666, 0);
-        if (c->semr[p] == SEM_FAILED || c->semw[p] == SEM_FAILED) return LGN_E_SYS;
+        if (c->semr[p] == SEM_FAILED || c->semw[p] == SEM_FAILED) { lgn_ipc_client_close(c); return LGN_E_SYS; }
         sem_post(c->semr[p]);                                                      // both slots start free (:91)
     }
     *out = c;
@@ -205,8 +206,7 @@ int lgn_ipc_client_close(lgn_ipc_client* c)
         if (c->semw[p] && c->semw[p] != SEM_FAILED) sem_close(c->semw[p]);
     }
     cudaGetLastError();
-    if (c->shm) munmap(c->shm, sizeof(ShmLayout));
-    if (c->fd > 0) close(c->fd);
+    if (c->shm) { munmap(c->shm, sizeof(ShmLayout)); close(c->fd); }
     delete c;
     return LGN_OK;
 }
