@@ -434,6 +434,18 @@ def run_b200(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    peer_debug = None
+    if os.environ.get("LGN_BENCH_PEER_DEBUG") and kg_bind > 1:
+        # diagnostic (NVLink tier): the probe's plain LDG loop over THIS process's shard mappings,
+        # all ranks at once, before anything else runs: uniform rows over the whole shard and over its first 64 Ki rows
+        peer_debug = {}
+        n_dbg = min(200_000, r.capacity)
+        for tag, rows in (("whole_shard", cap), ("first_64Ki_rows", min(cap, 65536))):
+            dist.barrier()
+            ms_dbg = r.debug_shard_read(n_dbg, rows, peers_only=True, repeats=6, stream=lp[0])
+            peer_debug[tag + "_GBps"] = n_dbg * 4 * D / (ms_dbg / 1e3) / 1e9
+        sys.stderr.write("rank %d peer_debug %s\n" % (rank, peer_debug))
+        dist.barrier()
 
     # ---- the timed step -------------------------------------------------------------------
     def step_resident(i):
@@ -686,6 +698,8 @@ def run_b200(args):
                       "presampling_epoch_s": t_pre, "tier_rows": tiers,
                       "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unprofiled": host_enqueue_plain_ms,
                       "ms_per_step_instrumented_pass": ms_prof / K}}
+    if peer_debug is not None:
+        line["extra"]["peer_debug"] = peer_debug
 
     if not args.no_train_epoch:
         try:

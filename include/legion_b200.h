@@ -183,6 +183,13 @@ int lgn_profile_collect(lgn_ctx* ctx, double ms_by_kind[4], int64_t calls_by_kin
 /* raw timeline: up to max_records rows of {kind, slot, begin_ms, end_ms} relative to the first record; returns
  * the number of rows through *n_out.  Does not reset. */
 int lgn_profile_timeline(lgn_ctx* ctx, double* rows4, int32_t max_records, int32_t* n_out);
+/* diagnostic: gathers n_rows pseudo-random rows (row index < rows_per_shard, uniformly spread over the bound
+ * cache shards; peers_only != 0 skips this GPU's own shard) into `slot`'s feature buffer with the plain 128-bit
+ * LDG loop of tools/peer_probe.cu -- no id list, no slot table, no cache hints -- `repeats` times, and returns
+ * the average launch time.  Separates "the mapping is slow" from "the gather kernel / its data is slow" when
+ * the NVLink tier under-performs.  No reference counterpart. */
+int lgn_debug_shard_read(lgn_ctx* ctx, void* stream, int32_t slot, int64_t n_rows, int64_t rows_per_shard, int32_t peers_only,
+                         int32_t repeats, double* avg_ms);
 
 /* ------------------------------------------------------------------ planner
  * presampling statistics and cache construction (GPUCache.cu:578-826). */

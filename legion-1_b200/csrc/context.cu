@@ -456,6 +456,31 @@ int lgn_profile_timeline(lgn_ctx* c, double* rows, int32_t max_records, int32_t*
     return LGN_OK;
 }
 
+int lgn_debug_shard_read(lgn_ctx* c, void* stream, int32_t slot, int64_t n_rows, int64_t rows_per_shard, int32_t peers_only,
+                         int32_t repeats, double* avg_ms)
+{
+    if (!c || !avg_ms || slot < 0 || slot >= c->n_lanes || n_rows <= 0 || rows_per_shard <= 0 || repeats <= 0) return LGN_E_ARG;
+    if (!c->feat.slot_of || c->feat.n_parts == 0 || c->cfg.feat_dim <= 0 || (c->cfg.feat_dim & 3) || c->cfg.feat_dim > 512) return LGN_E_STATE;
+    if (n_rows > c->max_rows || rows_per_shard > c->feat.cap || rows_per_shard > 0xffffffffLL) return LGN_E_CAPACITY;
+    if (peers_only && c->feat.n_parts < 2) return LGN_E_STATE;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    launch_debug_shard_read(c, s, slot, n_rows, rows_per_shard, peers_only != 0, 1u);       // warm-up
+    CK(cudaEventRecord(e0, s));
+    for (int i = 0; i < repeats; i++) launch_debug_shard_read(c, s, slot, n_rows, rows_per_shard, peers_only != 0, 0x9e3779b9u * (uint32_t)(i + 2));
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *avg_ms = (double)ms / repeats;
+    return LGN_OK;
+}
+
 // ---------------------------------------------------------------- hot path
 int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int32_t batch_size, int32_t counter)
 {

@@ -109,6 +109,7 @@ void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
 // gather.cu
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs);
 void gather_init_device();
+void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_rows, long long rows_per_shard, bool peers_only, uint32_t salt);
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,
                      float* dst, int n_sm, cudaStream_t s);
 }  // namespace lgn

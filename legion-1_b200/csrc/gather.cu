@@ -231,6 +231,50 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_row_copy(const int32_t* __re
     }
 }
 
+// diagnostic kernel (lgn_debug_shard_read): the probe's plain LDG loop over the context's own shard mappings
+struct DebugTabs { const float* tab[LGN_MAX_PARTS]; int n; };
+__device__ __forceinline__ uint32_t debug_mix(uint32_t x) { x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16; return x; }
+__global__ void __launch_bounds__(GATHER_THREADS) k_debug_shard_read(const __grid_constant__ DebugTabs tb, long long rows_per_shard, long long n_rows,
+                                                                     int dim, float* __restrict__ out, uint32_t salt)
+{
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * GATHER_THREADS + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * GATHER_THREADS) >> 5;
+    const int nvec = dim >> 2;
+    for (long long r0 = warp * U; r0 < n_rows; r0 += n_warps * U) {
+        uint4 v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long r = r0 + u;
+            if (r < n_rows) {
+                const uint32_t h = debug_mix((uint32_t)r ^ salt);
+                const uint4* sp = reinterpret_cast<const uint4*>(tb.tab[(h >> 20) % tb.n] + (long long)(h % (uint32_t)rows_per_shard) * dim);
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (lane + 32 * k < nvec) v[u][k] = __ldg(sp + lane + 32 * k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long r = r0 + u;
+            if (r < n_rows) {
+                uint4* d = reinterpret_cast<uint4*>(out + r * dim);
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (lane + 32 * k < nvec) d[lane + 32 * k] = v[u][k];
+            }
+        }
+    }
+}
+
+void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_rows, long long rows_per_shard, bool peers_only, uint32_t salt)
+{
+    DebugTabs tb;
+    tb.n = 0;
+    for (int i = 0; i < c->feat.n_parts; i++)
+        if (!peers_only || i != c->feat.my_part) tb.tab[tb.n++] = c->feat.shard_tab[i];
+    if (tb.n == 0) return;
+    k_debug_shard_read<<<c->n_sm * 3, GATHER_THREADS, 0, s>>>(tb, rows_per_shard, n_rows, c->cfg.feat_dim, c->pipe[pipe].features, salt);
+}
+
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
 {
     Pipe& p = c->pipe[c->cur_pipe];

@@ -171,6 +171,13 @@ class Runner:
     def status(self, stream=None):
         return lib().lgn_status(self.handle, _vp(stream))
 
+    def debug_shard_read(self, n_rows, rows_per_shard, peers_only=True, repeats=6, pipe=0, stream=None):
+        """diagnostic: average ms of a plain random row read out of the bound cache shards (lgn_debug_shard_read)."""
+        ms = C.c_double()
+        check(lib().lgn_debug_shard_read(self.handle, _vp(stream), C.c_int32(pipe), C.c_int64(n_rows), C.c_int64(rows_per_shard),
+                                         C.c_int32(1 if peers_only else 0), C.c_int32(repeats), C.byref(ms)), "lgn_debug_shard_read")
+        return ms.value
+
     def hotness(self):
         a, b = C.c_void_p(), C.c_void_p()
         check(lib().lgn_hotness(self.handle, C.byref(a), C.byref(b)), "lgn_hotness")

@@ -241,6 +241,36 @@ def test_hybrid_placement_gather(kg, frac_repl, frac_shard):
         r.close()
 
 
+def test_debug_shard_read_copies_shard_rows():
+    """lgn_debug_shard_read (diagnostic entry point): every output row must be a bit-exact copy of SOME row of the
+    bound shards, peers_only must leave this GPU's own shard out, and argument checks must hold."""
+    import legion_b200 as L
+    dim, kg, cap = 64, 4, 500
+    rng = np.random.default_rng(5)
+    shards_h = [(rng.random((cap, dim), dtype=np.float32) * 0.5 + j).astype(np.float32) for j in range(kg)]   # shard j holds values in [j, j+0.5]
+    shards_d = [L.DevArray.from_numpy(x) for x in shards_h]
+    n_nodes = cap * kg
+    slot = L.DevArray.from_numpy(np.arange(n_nodes, dtype=np.int32))
+    base = L.DevArray.from_numpy(np.zeros((n_nodes, dim), np.float32))
+    r = L.Runner(n_nodes, dim, 256, [4], part=1)
+    r.bind_features(base)
+    r.bind_feature_cache(shards_d, slot, cap)
+    n_rows = 1000
+    for peers_only in (False, True):
+        ms = r.debug_shard_read(n_rows, cap, peers_only=peers_only, repeats=2)
+        assert ms > 0
+        out = L.DevArray((n_rows, dim), np.float32, ptr=r.view(0).features, owner=False).numpy()
+        owner = np.floor(out[:, 0]).astype(int)
+        assert ((owner >= 0) & (owner < kg)).all()
+        if peers_only:
+            assert (owner != 1).all()
+        table = {j: {row.tobytes() for row in shards_h[j]} for j in range(kg)}
+        assert all(out[i].tobytes() in table[owner[i]] for i in range(0, n_rows, 7))
+    with pytest.raises(L._lib.LegionError):
+        r.debug_shard_read(n_rows, cap + 1)
+    r.close()
+
+
 def test_presampling_hotness_and_planner(c1):
     """presampling epoch: node / topology hotness, max ids, hot order, shards, cost model."""
     import legion_b200 as L

@@ -27,6 +27,8 @@ try:
     d = json.load(open(sys.argv[1])); r = d["roofline"]
     print("== bench %-14s %8.3f ms/step  alone %7.0f us  hit-mix %.3f  %6.0f GB/s/GPU" % (
         sys.argv[2], d["ms_per_step"], r["alone"]["avg_launch_us"], r["hit_mix"]["frac"], r["hit_mix"]["achieved_payload_GBps_per_gpu"]))
+    if "peer_debug" in d.get("extra", {}):
+        print("   in-process plain shard read, GB/s per GPU:", d["extra"]["peer_debug"])
 except Exception as e:
     print("== bench %s failed: %r" % (sys.argv[2], e))
 PY
@@ -37,4 +39,4 @@ probe alloc2g5 PROBE_ALLOC_MB=2441      # the product's 2.56 GB shard size
 bench gloo LGN_BENCH_BACKEND=gloo       # no NCCL communicator in the process at all
 bench nohot LGN_BENCH_HOTNESS=none      # NCCL communicator, but no large all-reduce
 bench hosthot LGN_BENCH_HOTNESS=host    # hotness reduced through host memory
-bench control A=1
+bench control LGN_BENCH_PEER_DEBUG=1   # also prints the in-process plain shard read (extra.peer_debug, stderr)
