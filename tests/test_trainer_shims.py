@@ -56,3 +56,24 @@ def test_sage_model_trains_and_accuracy_metric():
     with torch.no_grad():
         acc = m(torch.softmax(model([trainer.make_block(s1, d1, n9, n7), trainer.make_block(s2, d2, 30, n5)], x), 1), y)
     assert 0.0 <= float(acc) <= 1.0 and float(m.compute()) == float(acc)
+
+
+def test_spmm_aggregation_equals_index_add(monkeypatch):
+    """LEGION_SHIM_SPMM=1 (CSR SpMM) must give the same sums and the same input gradient as index_add_ (fp32, 1e-5)."""
+    import legion_b200  # noqa: F401
+    from legion_b200 import trainer
+    from dgl import heterograph
+    src, dst, n_src, n_dst = _block(300, 90, 2500, 3)
+    x = torch.randn(n_src, 20, requires_grad=True)
+    g = torch.randn(n_dst, 20)
+    res = []
+    for flag in (False, True):
+        monkeypatch.setattr(heterograph, "_USE_SPMM", flag)
+        blk = trainer.make_block(src, dst, n_src, n_dst)
+        out = blk.sum_messages(x)
+        (gx,) = torch.autograd.grad(out, x, g)
+        res.append((out.detach(), gx))
+    assert torch.allclose(res[0][0], res[1][0], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-5, rtol=1e-5)
+    empty = trainer.make_block(src[:0], dst[:0], n_src, n_dst)
+    assert float(empty.sum_messages(x.detach()).abs().sum()) == 0.0
