@@ -256,3 +256,24 @@ def test_synth_numpy_equals_torch():
     assert np.array_equal(a.train_ids, b.train_ids.numpy())
     assert abs(a.n_edges / a.n_nodes - 12.0) < 0.5
     assert torch.equal(b.labels, torch.from_numpy(a.labels))
+
+
+def test_dataset_files_round_trip(tmp_path):
+    """the on-disk format the reference loader reads (GPUGraphStore.cu:254-301): raw little-endian arrays with the
+    reference's file names, sizes implied by the 11-field meta_config; write -> read must be bit-exact."""
+    import legion_b200 as L
+    from legion_b200 import dataset_io
+    d = L.synth.make_dataset(3000, 6.0, 12, n_class=5)
+    data = str(tmp_path / "data")
+    dataset_io.write_dataset(data, d)
+    line = dataset_io.write_meta_config(str(tmp_path), data, d, 64, 10**6, 2)
+    f = line.split()
+    assert len(f) == 11 and f[0].endswith("/") and [int(x) for x in f[1:8]] == [64, d.n_nodes, d.n_edges, d.dim, len(d.train_ids), len(d.valid_ids), len(d.test_ids)]
+    sizes = {"edge_src": 8 * (d.n_nodes + 1), "edge_dst": 4 * d.n_edges, "features": 4 * d.n_nodes * d.dim, "labels": 4 * d.n_nodes,
+             "trainingset": 4 * len(d.train_ids), "validationset": 4 * len(d.valid_ids), "testingset": 4 * len(d.test_ids)}
+    for name, n in sizes.items():
+        assert os.path.getsize(os.path.join(data, name)) == n, name
+    back = dataset_io.read_dataset(data, d.n_nodes, d.n_edges, d.dim, len(d.train_ids), len(d.valid_ids), len(d.test_ids))
+    for k in ("indptr", "indices", "labels", "train_ids", "valid_ids", "test_ids"):
+        assert np.array_equal(getattr(back, k), getattr(d, k)), k
+    assert np.array_equal(back.features.view(np.uint32), d.features.view(np.uint32))
