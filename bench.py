@@ -412,10 +412,29 @@ def run_b200(args):
     r.bind_features(base)
     if early_shard is not None and early_shard.shape != (cap, D):
         early_shard = None
+    # LGN_BENCH_SHARD_ALLOC=vmm: shards created with the VMM API and shared as file descriptors (lgn_shared_*) instead
+    # of cudaMalloc + legacy CUDA IPC handles (diagnostic alternative for the NVLink tier)
+    use_vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm" and kg_bind > 1
+    shard_fd = mapped_bytes = None
+    if use_vmm:
+        early_shard, shard_fd, mapped_bytes = L.shared_alloc((cap, D), np.float32)
     my_shard = L.fill_feature_shard_hybrid(order, cap, kg_bind, part_bind, n_repl, ds.features, D, out=early_shard)
     shards = [my_shard]
     imported = []
-    if kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
+    if kg_bind > 1 and use_vmm:
+        torch.cuda.synchronize()
+        fds = cluster.exchange_fds(dist, shard_fd)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(mapped_bytes))
+        shards = []
+        for j in range(world):
+            if j == rank:
+                shards.append(my_shard)
+            else:
+                shards.append(L.shared_import(fds[j], sizes[j], (cap, D), np.float32))
+                os.close(fds[j])
+        os.close(shard_fd)
+    elif kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
         import ctypes as C
         h = (C.c_uint8 * 64)()
         L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(my_shard.ptr), h), "ipc_export")

@@ -71,6 +71,16 @@ int lgn_enable_peer_access(int32_t n_devices);
 int lgn_ipc_export(void* dev_ptr, uint8_t handle[64]);
 int lgn_ipc_import(const uint8_t handle[64], void** dev_ptr);
 int lgn_ipc_close(void* dev_ptr);
+/* Cross-process shards through the CUDA virtual-memory-management API (B200 extension; no reference counterpart:
+ * the reference is one process driving all GPUs).  lgn_shared_alloc creates device memory on the current device
+ * whose shareable handle is a POSIX file descriptor (*fd_out, to be passed to the peer processes over a Unix
+ * socket and closed by the caller afterwards) and maps it read/write for the current device; *mapped_bytes is
+ * the size rounded up to the allocation granularity, which the importer must pass back.  lgn_shared_import maps
+ * such a descriptor into the calling process and grants the CALLING process's current device read/write access
+ * (the NVLink peer mapping).  lgn_shared_free unmaps and releases either kind. */
+int lgn_shared_alloc(void** dev_ptr, int64_t bytes, int32_t* fd_out, int64_t* mapped_bytes);
+int lgn_shared_import(int32_t fd, int64_t mapped_bytes, void** dev_ptr);
+int lgn_shared_free(void* dev_ptr);
 
 /* ------------------------------------------------------------------ context
  * One context per GPU = the reference's GPURunner + its GPUMemoryPool

@@ -54,6 +54,57 @@ def exchange_handles(dist, handle_bytes):
     return out
 
 
+def exchange_fds(dist, fd, tag="shard"):
+    """every rank contributes one open file descriptor (the shareable handle of lgn_shared_alloc) and receives a
+    duplicate of every other rank's: descriptors cannot travel through torch.distributed, so each rank serves its own
+    over a Unix-domain socket (SCM_RIGHTS).  Returns the list indexed by rank (own entry = the descriptor passed in);
+    the caller closes the received duplicates after importing them.  Single node only, like the NVLink clique."""
+    import os
+    import socket
+    import tempfile
+    import threading
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    if world == 1:
+        return [fd]
+    rank = dist.get_rank()
+    token = [os.urandom(6).hex() if rank == 0 else None]
+    dist.broadcast_object_list(token, src=0)
+    path = lambda j: os.path.join(tempfile.gettempdir(), "lgn_%s_%s_%d.sock" % (tag, token[0], j))
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    if os.path.exists(path(rank)):
+        os.unlink(path(rank))
+    srv.bind(path(rank))
+    srv.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _addr = srv.accept()
+            with conn:
+                conn.recv(4)                                     # the requester's rank (informational)
+                socket.send_fds(conn, [b"f"], [fd])
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    dist.barrier()                                               # every listener is up
+    out = [None] * world
+    out[rank] = fd
+    for j in range(world):
+        if j == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+            c.connect(path(j))
+            c.sendall(int(rank).to_bytes(4, "little"))
+            _msg, fds, _flags, _addr = socket.recv_fds(c, 1, 1)
+            if len(fds) != 1:
+                raise RuntimeError("rank %d sent no descriptor" % j)
+            out[j] = fds[0]
+    th.join()
+    dist.barrier()
+    srv.close()
+    os.unlink(path(rank))
+    return out
+
+
 def slot_of_rank(i, cap, kg):
     """global slot of hot rank i: GPU i % kg, row i / kg (InitPair, GPUCache.cu:103-108)."""
     return (i % kg) * cap + i // kg

@@ -238,6 +238,27 @@ def fill_feature_shard(order, cap, kg, j, features, dim, stream=None, out=None):
     return shard
 
 
+def shared_alloc(shape, dtype):
+    """device array other processes can map (lgn_shared_alloc): returns (array, fd, mapped_bytes); close fd after the exchange,
+    release the array with shared_free."""
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    p, fd, mapped = C.c_void_p(), C.c_int32(-1), C.c_int64(0)
+    check(lib().lgn_shared_alloc(C.byref(p), C.c_int64(max(1, nbytes)), C.byref(fd), C.byref(mapped)), "lgn_shared_alloc")
+    return DevArray(shape, dtype, ptr=p.value, owner=False), fd.value, mapped.value
+
+
+def shared_import(fd, mapped_bytes, shape, dtype):
+    """map another process's shared_alloc array for THIS process's current device (lgn_shared_import)."""
+    p = C.c_void_p()
+    check(lib().lgn_shared_import(C.c_int32(fd), C.c_int64(mapped_bytes), C.byref(p)), "lgn_shared_import")
+    return DevArray(tuple(int(x) for x in np.atleast_1d(shape)), dtype, ptr=p.value, owner=False)
+
+
+def shared_free(arr):
+    check(lib().lgn_shared_free(C.c_void_p(arr.ptr)), "lgn_shared_free")
+
+
 def place_hybrid(order, cap, kg, n_repl, my_part, stream=None):
     """B200 extension: n_repl hottest ranks replicated on every GPU, the rest partitioned (lgn_place_hybrid)."""
     n = order.shape[0]

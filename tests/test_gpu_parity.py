@@ -3,6 +3,8 @@ same seeded inputs.  Integer / index / byte work throughout => every comparison 
 Edge cases follow the reference's own branches: padded (-1) seeds (Kernels.cu:81-83,385),
 clamped last batch (Kernels.cu:224), zero-degree nodes (Kernels.cu:399), duplicates in the
 frontier (Kernels.cu:371-373), cache hit / miss tiers (Kernels.cu:692-699)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -269,6 +271,34 @@ def test_debug_shard_read_copies_shard_rows():
     with pytest.raises(L._lib.LegionError):
         r.debug_shard_read(n_rows, cap + 1)
     r.close()
+
+
+def test_shared_allocation_round_trip():
+    """lgn_shared_alloc / lgn_shared_import / lgn_shared_free (VMM shards shared as file descriptors): a second mapping
+    of the same allocation, imported through the descriptor, must see the bytes written through the first one, and a
+    gather must read it like any other shard."""
+    import legion_b200 as L
+    rows, dim = 3000, 32
+    a, fd, mapped = L.shared_alloc((rows, dim), np.float32)
+    assert fd >= 0 and mapped >= rows * dim * 4
+    want = np.random.default_rng(2).random((rows, dim), dtype=np.float32)
+    import ctypes as C
+    L._lib.check(L.lib().lgn_copy_h2d(C.c_void_p(a.ptr), want.ctypes.data_as(C.c_void_p), C.c_int64(want.nbytes)), "h2d")
+    b = L.shared_import(fd, mapped, (rows, dim), np.float32)
+    os.close(fd)
+    assert b.ptr != a.ptr
+    assert np.array_equal(b.numpy().view(np.uint32), want.view(np.uint32))
+    # the imported mapping as a cache shard
+    r = L.Runner(rows, dim, 128, [3])
+    r.bind_features(L.DevArray.from_numpy(np.zeros((rows, dim), np.float32)))
+    r.bind_feature_cache([b], L.DevArray.from_numpy(np.arange(rows, dtype=np.int32)), rows)
+    ms = r.debug_shard_read(400, rows, peers_only=False, repeats=1)
+    assert ms > 0
+    r.close()
+    L.shared_free(b)
+    L.shared_free(a)
+    with pytest.raises(L._lib.LegionError):
+        L.shared_free(a)
 
 
 def test_presampling_hotness_and_planner(c1):

@@ -53,6 +53,18 @@ def _worker(rank, world, port, q):
         shard = O.fill_feature_shard(order, cap, world, rank, d.features)
         handles = cluster.exchange_handles(dist, bytes([rank]) * 64)       # stand-in for lgn_ipc_export's 64 bytes
         assert [h[0] for h in handles] == list(range(world)) and all(len(h) == 64 for h in handles)
+        # descriptor exchange (shareable handles of lgn_shared_alloc travel as file descriptors over Unix sockets):
+        # every rank offers a temp file holding its rank, and must read every other rank's content through the duplicate
+        import tempfile
+        with tempfile.TemporaryFile() as tf:
+            tf.write(b"shard-of-rank-%d" % rank)
+            tf.flush()
+            fds = cluster.exchange_fds(dist, tf.fileno(), tag="t")
+            assert fds[rank] == tf.fileno() and len(fds) == world
+            for j, fd in enumerate(fds):
+                assert os.pread(fd, 64, 0) == b"shard-of-rank-%d" % j
+                if j != rank:
+                    os.close(fd)
         shards = [None] * world
         dist.all_gather_object(shards, shard)
         batch = smp.sample(mine[:B], step=0)

@@ -39,4 +39,5 @@ probe alloc2g5 PROBE_ALLOC_MB=2441      # the product's 2.56 GB shard size
 bench gloo LGN_BENCH_BACKEND=gloo       # no NCCL communicator in the process at all
 bench nohot LGN_BENCH_HOTNESS=none      # NCCL communicator, but no large all-reduce
 bench hosthot LGN_BENCH_HOTNESS=host    # hotness reduced through host memory
+bench vmm LGN_BENCH_SHARD_ALLOC=vmm LGN_BENCH_PEER_DEBUG=1   # shards through cuMemCreate + fd + cuMemSetAccess instead of cudaIpc*
 bench control LGN_BENCH_PEER_DEBUG=1   # also prints the in-process plain shard read (extra.peer_debug, stderr)
