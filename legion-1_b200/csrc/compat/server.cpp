@@ -414,6 +414,12 @@ public:
                 runners_[i]->SyncAll();
             });
         for (auto& t : th) t.join();
+        // hash dedup (large graphs): size the per-batch table for what presampling saw instead of the worst case,
+        // so that it stays L2-resident (2.5x the largest batch inside the call; no-op for the direct map)
+        for (int i = 0; i < n_; i++) {
+            const int32_t seen = lgn_max_ids(ctx_[i], nullptr);
+            if (seen > 0) LGN_DIE(lgn_set_dedup_capacity(ctx_[i], seen), "lgn_set_dedup_capacity");
+        }
         int kg = cache_agg_mode == 1 ? 2 : cache_agg_mode == 2 ? 4 : cache_agg_mode == 3 ? 8 : 1;   // GPUCache.cu:593-607
         if (kg > n_) {   // the reference computes Kc = 0 here and serves without any cache
             std::cout << "cache aggregate mode " << cache_agg_mode << " asks for " << kg << " GPUs per clique, only " << n_ << " present: using " << n_ << "\n";
