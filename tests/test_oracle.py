@@ -277,3 +277,20 @@ def test_dataset_files_round_trip(tmp_path):
     for k in ("indptr", "indices", "labels", "train_ids", "valid_ids", "test_ids"):
         assert np.array_equal(getattr(back, k), getattr(d, k)), k
     assert np.array_equal(back.features.view(np.uint32), d.features.view(np.uint32))
+
+
+def test_launcher_writes_reference_meta_config(tmp_path, monkeypatch, capsys):
+    """legion_server.py keeps the reference launcher's command line (legion_server.py:72-85): dataset table, 11-field
+    meta_config (path batch vertices edges dim train valid test cache epochs partition) and the clique-mode rule."""
+    import legion_b200  # noqa: F401
+    from legion_b200 import legion_server
+    monkeypatch.chdir(tmp_path)
+    assert legion_server.main(["--dataset", "PR", "--dataset_path", "/data", "--gpu_number", "4", "--epoch", "3", "--dry_run"]) == 0
+    f = open(tmp_path / "meta_config").read().split()
+    assert f == ["/data/products/", "8000", "2449029", "123718280", "100", "196615", "39323", "2213091", "38000000000", "3", "0"]
+    assert capsys.readouterr().out.split()[-2:] == ["4", "1"]          # >= 2 GPUs with NVLink -> 2 GPUs per clique (reference rule)
+    assert legion_server.main(["--dataset", "PA", "--gpu_number", "8", "--cache_agg_mode", "3", "--usenvlink", "0", "--dry_run"]) == 0
+    f = open(tmp_path / "meta_config").read().split()
+    assert f[2:5] == ["111059956", "1615685872", "128"] and f[-1] == "1"
+    assert capsys.readouterr().out.split()[-2:] == ["8", "3"]
+    assert legion_server.main(["--dataset", "nope", "--dry_run"]) == 2
