@@ -1,6 +1,7 @@
 """SAGEConv (mean) and GraphConv (norm='both') with DGL's parameterisation and forward semantics on blocks."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 class SAGEConv(nn.Module):
@@ -24,11 +25,10 @@ class SAGEConv(nn.Module):
         lin_before = self.fc_neigh.in_features > self.fc_neigh.out_features      # DGL applies the linear first when it shrinks
         msg = self.fc_neigh(h_src) if lin_before else h_src
         h_neigh = block.sum_messages(msg) / deg
-        if not lin_before:
-            h_neigh = self.fc_neigh(h_neigh)
-        out = self.fc_self(h_dst) + h_neigh
-        if self.bias is not None:
-            out = out + self.bias
+        # W_self h_v + b in one GEMM epilogue, W_neigh mean(h_u) accumulated into it by the second GEMM (beta = 1):
+        # no separate [n_dst x out] add passes
+        out = F.linear(h_dst, self.fc_self.weight, self.bias)
+        out = out + h_neigh if lin_before else torch.addmm(out, h_neigh, self.fc_neigh.weight.t())
         if self.activation is not None:
             out = self.activation(out)
         if self.norm is not None:
