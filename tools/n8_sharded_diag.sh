@@ -34,10 +34,11 @@ except Exception as e:
 PY
 }
 
-probe alloc8g A=1                       # 8 GiB tables + product-like variants (hints / skew / lookup)
-probe alloc2g5 PROBE_ALLOC_MB=2441      # the product's 2.56 GB shard size
-bench gloo LGN_BENCH_BACKEND=gloo       # no NCCL communicator in the process at all
-bench nohot LGN_BENCH_HOTNESS=none      # NCCL communicator, but no large all-reduce
-bench hosthot LGN_BENCH_HOTNESS=host    # hotness reduced through host memory
-bench vmm LGN_BENCH_SHARD_ALLOC=vmm LGN_BENCH_PEER_DEBUG=1   # shards through cuMemCreate + fd + cuMemSetAccess instead of cudaIpc*
-bench control LGN_BENCH_PEER_DEBUG=1   # also prints the in-process plain shard read (extra.peer_debug, stderr)
+bench control LGN_BENCH_PEER_DEBUG=1     # reproduces the defect; extra.peer_debug = the probe's plain loop over THIS process's mappings
+bench gloo LGN_BENCH_BACKEND=gloo LGN_BENCH_PEER_DEBUG=1   # no NCCL communicator in the process at all
+bench vmm LGN_BENCH_SHARD_ALLOC=vmm LGN_BENCH_PEER_DEBUG=1  # shards through cuMemCreate + fd + cuMemSetAccess instead of cudaIpc*
+bench nonvls NCCL_NVLS_ENABLE=0          # NCCL without NVLink SHARP multicast
+bench nohot LGN_BENCH_HOTNESS=none       # NCCL communicator, but no large all-reduce
+bench hosthot LGN_BENCH_HOTNESS=host     # hotness reduced through host memory
+probe alloc8g A=1                        # 8 GiB tables + product-like variants (hints / skew / lookup)
+probe alloc2g5 PROBE_ALLOC_MB=2441       # the product's 2.56 GB shard size
