@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- Legion mini-batch hot path on N B200s (one process per GPU).
 
-A "step" is one mini-batch of the pipeline on every rank: batch generation, k-hop neighbour
-sampling, dedup/relabel and feature extraction from the NVLink-clique-partitioned cache.
-Headline metric (BASELINE.json): sampled edges/s (whole job), with feature-extract GB/s and a
-GraphSAGE data-loading epoch estimate in `extra`.  Workload at every N: BASELINE.json configs[1],
-the ogbn-products-shaped synthetic graph (2,449,029 nodes, ~61.9 M edges, 100-d features),
-batch 8000 per GPU, fanout [25,10] -- weak scaling: each rank draws its own `tid % N` seed
-partition, the feature cache is sharded over the N GPUs and peer shards are read with P2P loads.
+A "step" is one mini-batch of the pipeline on every rank: batch generation, k-hop neighbour sampling, dedup /
+relabel and feature extraction from the NVLink-clique cache.  Headline metric (BASELINE.json): sampled edges/s
+(whole job), with feature-extract GB/s and GraphSAGE epoch seconds in `extra`.
+
+Workload at every N: BASELINE.json configs[2], the ogbn-papers100M-shaped synthetic graph (111,059,956 nodes,
+~1.6 G edges, 128-d features; it fits one B200), batch 8000 per GPU, fanout [25,10] -- weak scaling: each rank
+draws its own `tid % N` seed partition.  Feature cache over the N GPUs with the launcher's per-GPU budget
+(legion_server.py: 38 GB): `value` is measured with the default placement (hottest rows replicated, the rest
+partitioned round-robin over the clique), `extra.sharded` with the reference's pure round-robin partition
+(GPUCache.cu:103-108), where (N-1)/N of the rows cross NVLink as in-kernel P2P loads.  The timed epoch is not the
+presampled one (Philox counter word 1 = epoch), and before any timing every rank checks one mini-batch bit for bit
+against the CPU oracle through the real peer mappings (`parity_checked`).
 
   python bench.py --gpus 1 --steps 50 --warmup 10
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference        # CPU arm: the oracle port of the reference path
+  python bench.py --impl reference        # CPU arm: the oracle port of the reference path on all host cores
+  python bench.py --config C2             # ogbn-products shape (BASELINE.json configs[1])
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -30,7 +37,7 @@ if ROOT not in sys.path:
 SHAPE_NAME = {"C1": "100K-node", "C2": "ogbn-products", "C3": "ogbn-papers100M", "C4": "UK-Union", "C5": "Friendster"}
 METRIC = "sampled edges/s"
 UNIT = "edges/s"
-
+NVLINK_NOMINAL = 900.0      # GB/s per direction per GPU (NVLink 5)
 
 _real_stdout = None
 
@@ -41,22 +48,30 @@ def emit(line):
     out.flush()
 
 
+def log(msg):
+    sys.stderr.write(msg + "\n")
+    sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default="C3")
     ap.add_argument("--rng", default="philox", choices=["philox", "minstd"])
-    ap.add_argument("--cache-frac", type=float, default=1.0, help="fraction of rows cached in HBM (rest: host UVA tier)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--cache-frac", type=float, default=1.0, help="fraction of rows that may be cached in HBM at all (rest: host UVA tier)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nodes", type=int, default=0, help="override node count (debug)")
     ap.add_argument("--placement", default="hybrid", choices=["sharded", "hybrid", "replicated"],
                     help="feature cache over the N GPUs: reference round-robin partition | hot rows replicated + rest partitioned | all replicated")
-    ap.add_argument("--gpu-cache-gb", type=float, default=38.0, help="per-GPU feature-cache budget (legion_server.py default 38 GB)")
+    ap.add_argument("--gpu-cache-gb", type=float, default=0.0,
+                    help="per-GPU feature-cache budget; 0 = the launcher's 38 GB when N > 1 (legion_server.py), the whole table when N = 1")
+    ap.add_argument("--no-extra-sharded", action="store_true", help="skip the second measurement with the reference partition (N > 1)")
     ap.add_argument("--no-train-epoch", action="store_true", help="skip the GraphSAGE epoch-time leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing oracle check (debug)")
     ap.add_argument("--probe", action="store_true", help="debug: time sampling-only and gather-only loops")
     ap.add_argument("--lanes", type=int, default=4, help="mini-batches in flight per GPU (batch slots)")
     return ap.parse_args()
@@ -116,6 +131,47 @@ def workload(args):
     return cfg
 
 
+def workload_string(args, cfg, n_edges):
+    """identical in both arms (the driver compares it)."""
+    return (f"{args.config} {SHAPE_NAME.get(args.config, 'synthetic')}-shaped synthetic ({cfg['n_nodes']} nodes, {n_edges} edges, "
+            f"{cfg['dim']}-d), GraphSAGE fanout {cfg['fanout']}, batch {cfg['batch']}/GPU, rng {args.rng}, sampling + feature extraction")
+
+
+def _chunked_to_host(t, D):
+    """device tensor [N, D] -> numpy, in 256 MB pieces (no second full-size staging copy)."""
+    n = t.shape[0]
+    out = np.empty((n, D), np.float32)
+    rows = max(1, (1 << 28) // (4 * D))
+    for lo in range(0, n, rows):
+        out[lo:lo + rows] = t[lo:lo + rows].cpu().numpy()
+    return out
+
+
+def host_dataset(cfg, want_features=True):
+    """the synthetic dataset as numpy arrays; built on the GPU when there is one (the numpy build of 1.6 G edges takes
+    minutes), bit-identical either way (tests/test_oracle.py::test_synth_numpy_equals_torch)."""
+    import legion_b200 as L
+    N, D = cfg["n_nodes"], cfg["dim"]
+    try:
+        import torch
+        cuda = torch.cuda.is_available()
+    except Exception:      # noqa: BLE001
+        cuda = False
+    if not cuda or N < 5_000_000:
+        return L.synth.make_dataset(N, cfg["avg_deg"], D, n_class=cfg["n_class"], with_features=want_features)
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    dmin = L.synth.calibrate_dmin(cfg["avg_deg"], N)
+    ds = L.synth.make_dataset(N, cfg["avg_deg"], D, n_class=cfg["n_class"], backend="torch", device=dev, dmin_fp=dmin,
+                              with_features=want_features)
+    hd = L.synth.Dataset(n_nodes=N, n_edges=ds.n_edges, dim=D, n_class=cfg["n_class"], indptr=ds.indptr.cpu().numpy(),
+                         indices=ds.indices.cpu().numpy(), labels=ds.labels.cpu().numpy(), train_ids=ds.train_ids.cpu().numpy(),
+                         features=_chunked_to_host(ds.features, D) if want_features else None)
+    del ds
+    torch.cuda.empty_cache()
+    return hd
+
+
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path, all host threads, bounded sample
 # ------------------------------------------------------------------------------------------
@@ -123,7 +179,7 @@ _cpu_state = {}
 
 
 def cpu_leg(ds, cfg, seconds, steps_cap, rng_mode, seed, first_step=0):
-    """returns (edges/s, GB/s, n_batches, cores).  Same semantics as the GPU path; gathers rows by
+    """returns (edges/s, GB/s, n_batches, cores, seconds).  Same semantics as the GPU path; gathers rows by
     memcpy from the host feature matrix (the reference has no CPU path of its own: SURVEY 8d)."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
@@ -141,7 +197,7 @@ def cpu_leg(ds, cfg, seconds, steps_cap, rng_mode, seed, first_step=0):
     for it in range(steps_cap):          # cycles over the epoch's batches until the time budget is spent
         step = (first_step + it) % epoch_steps
         seeds = train[step * B:(step + 1) * B]
-        o = smp.sample(seeds, step=step)
+        o = smp.sample(seeds, step=step, epoch=1)
         total = int(o["nc"][0])
         O.gather(o["sampled_ids"], 0, total, None, 1, [], ds.features, out, n_threads=cores)
         edges += int(o["ec"][0]); rows += total; done += 1
@@ -151,11 +207,13 @@ def cpu_leg(ds, cfg, seconds, steps_cap, rng_mode, seed, first_step=0):
     return edges / dt, rows * ds.dim * 4 / dt / 1e9, done, cores, dt
 
 
-def reference_gpu_leg(ds, cfg, n_batches=20):
+def reference_gpu_leg(n_batches=20):
     """The reference's OWN kernels (Kernels.cu, GPUCache.cu, ... compiled unmodified for sm_100a into oracle/_ref by
     oracle/ref_harness) driven through its own operator sequence on this GPU: presampling epoch, CandidateSelection /
-    CostModel / FillUp, then n steady-state batches.  Informational: 'the kernel to beat' of BASELINE.md section 3."""
-    import ctypes as C
+    CostModel / FillUp, then n steady-state batches.  Informational: 'the kernel to beat' of BASELINE.md section 3.
+    Always on the C2 (ogbn-products) shape: the harness keeps the reference's pinned-host dataset and sweeps four cache
+    budgets, which would take minutes at papers100M size."""
+    import legion_b200 as L
     so = os.path.join(ROOT, "oracle", "_ref", "libref_legion.so")
     if not os.path.exists(so):
         return {"unavailable": "oracle/_ref/libref_legion.so not built"}
@@ -165,6 +223,8 @@ def reference_gpu_leg(ds, cfg, n_batches=20):
             return {"unavailable": "no CUDA device"}
     except Exception as e:      # noqa: BLE001
         return {"unavailable": repr(e)[:100]}
+    cfg = dict(L.synth.CONFIGS["C2"])
+    ds = L.synth.make_dataset(cfg["n_nodes"], cfg["avg_deg"], cfg["dim"], n_class=cfg["n_class"])
     lib = C.CDLL(so)
     lib.ref_create.restype = C.c_void_p
     p = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -201,42 +261,44 @@ def reference_gpu_leg(ds, cfg, n_batches=20):
                "presampling_epoch_s": t_pre}
         if best is None or res["ms_per_step"] < best["ms_per_step"]:
             best = res
-    best["note"] = ("reference kernels recompiled unmodified for sm_100a (upstream targets sm_80), its own operator sequence and cache "
-                    "planner, minstd stream; fastest of 4 cache budgets (its cost model caches a single tier once everything fits)")
+    best["workload"] = "C2 ogbn-products-shaped synthetic, batch 8000, fanout [25, 10] (1 GPU)"
+    best["note"] = ("reference kernels recompiled unmodified for sm_100a (upstream targets sm_80), its own operator sequence on its two "
+                    "event-chained streams (Server.cu:301-328) and its cache planner, minstd stream; fastest of 4 cache budgets (its cost "
+                    "model caches a single tier once everything fits)")
     return best
 
 
 def run_reference(args):
-    """--impl reference: the reference's own semantics on the host cores (oracle port)."""
+    """--impl reference: the reference's own semantics on the host cores (oracle port; the reference has no CPU path and its
+    GPU server needs MSR access for Intel PCM).  Each step = one mini-batch (a bounded sample of the epoch)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import legion_b200 as L
     from oracle import oracle as O
     cfg = workload(args)
-    ds = L.synth.make_dataset(cfg["n_nodes"], cfg["avg_deg"], cfg["dim"], n_class=cfg["n_class"])
+    ds = host_dataset(cfg)
     mode = O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD
-    per_step_budget = 8.0
-    # warm-up + K steps, each step = a bounded sample (1 batch) of the workload
-    for _ in range(min(args.warmup, 2)):
-        cpu_leg(ds, cfg, per_step_budget, 1, mode, 42)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    for i in range(W):
+        cpu_leg(ds, cfg, 1e9, 1, mode, 42, first_step=i)
     t_edges, t_time, gbs = 0.0, 0.0, []
-    k = max(1, min(args.steps, 10))
-    for i in range(k):
-        eps, gb, n, cores, dt = cpu_leg(ds, cfg, per_step_budget, 1, mode, 42, first_step=i)
+    for i in range(K):
+        eps, gb, n, cores, dt = cpu_leg(ds, cfg, 1e9, 1, mode, 42, first_step=W + i)
         t_edges += eps * dt; t_time += dt; gbs.append(gb)
     value = t_edges / t_time
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
-            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * t_time / k, "higher_is_better": True, "scaling": "weak",
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": 1e3 * t_time / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
-            "config": {"workload": f"{args.config} {SHAPE_NAME.get(args.config, 'synthetic')}-shaped synthetic, batch {cfg['batch']}, fanout {cfg['fanout']}, "
-                                   f"{cfg['dim']}-d, CPU sampling+gather (oracle port of the reference path)"},
+            "config": {"workload": workload_string(args, cfg, ds.n_edges),
+                       "arm": "CPU sampling+gather, oracle port of the reference path, OpenMP on all host cores; one step = one mini-batch of one GPU's seed stream"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{k} steps x 1 batch of {cfg['batch']} seeds"},
+                             "sample": f"{K} steps x 1 batch of {cfg['batch']} seeds"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extra": {"feature_extract_GBps": float(np.mean(gbs))}}
+    del ds
+    _cpu_state.clear()
     try:
-        line["reference_gpu"] = reference_gpu_leg(ds, cfg)
+        line["reference_gpu"] = reference_gpu_leg()
     except Exception as e:      # noqa: BLE001
         line["reference_gpu"] = {"unavailable": repr(e)[:200]}
     emit(line)
@@ -246,7 +308,7 @@ def run_reference(args):
 # GraphSAGE epoch time (third part of the BASELINE metric): the reference trainer's structure
 # (legion_graphsage.py:36-89) fed by the pipeline, one process per GPU, DDP over NCCL
 # ------------------------------------------------------------------------------------------
-def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train_steps, epochs=2):
+def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train_steps, epochs=2, max_steps=400):
     import torch
     from legion_b200 import trainer
 
@@ -254,6 +316,7 @@ def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train
         def __init__(s, ptr, shape, ts):
             s.__cuda_array_interface__ = {"shape": shape, "typestr": ts, "data": (int(ptr), False), "version": 2}
 
+    steps = min(train_steps, max_steps)
     views = []
     for q in range(NL):          # zero-copy tensors over the lane's output buffers (what ipc_service.get_next hands out)
         v = r.view(q)
@@ -271,12 +334,13 @@ def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train
     done_ev = [None] * NL
     times, first, last = [], None, None
     for ep in range(epochs):
+        r.set_epoch(2 + ep)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        for i in range(train_steps + NL - 1):
-            if i < train_steps:
+        for i in range(steps + NL - 1):
+            if i < steps:
                 q = i % NL
                 if done_ev[q] is not None:
                     done_ev[q].synchronize()          # the trainer has finished reading this slot (ipc_service.synchronize())
@@ -304,18 +368,32 @@ def graphsage_epoch(L, r, dist, world, dev, lp, NL, B, D, n_class, n_hops, train
         if world > 1:
             dist.barrier()
         times.append(time.perf_counter() - t0)
-    return {"graphsage_epoch_s": times[-1], "graphsage_first_epoch_s": times[0], "graphsage_steps_per_epoch": train_steps,
-            "graphsage_model": f"{n_hops}-layer SAGEConv(mean) hidden 256, Adam, fp32, {'DDP' if world > 1 else 'single GPU'}",
+    scale = train_steps / steps
+    return {"graphsage_epoch_s": times[-1] * scale, "graphsage_first_epoch_s": times[0] * scale, "graphsage_steps_per_epoch": train_steps,
+            "graphsage_steps_timed": steps,
+            "graphsage_model": f"{n_hops}-layer SAGEConv(mean) hidden 256, Adam, fp32, {'DDP' if world > 1 else 'single GPU'}; in-process consumer of the "
+                               "batch slots (tools/server_e2e.py times the server binary + trainer processes over the IPC wire)",
             "graphsage_loss_first": first, "graphsage_loss_last": float(last)}
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+class Cache:
+    """one placement of the feature cache over the clique, bound to the runner."""
+
+    def __init__(self):
+        self.shards, self.imported, self.my_shard, self.slot_of = [], [], None, None
+        self.cap = self.n_repl = self.kg_bind = 0
+        self.placement = ""
+        self.vmm = False
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import legion_b200 as L
+    from legion_b200 import cluster
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -323,8 +401,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # LGN_BENCH_BACKEND=gloo: diagnostic run without any NCCL communicator in the process (DESIGN.md section 4,
-        # NVLink tier); the GraphSAGE/DDP leg needs NCCL and is skipped then
+        # LGN_BENCH_BACKEND=gloo: diagnostic run without any NCCL communicator in the process; the GraphSAGE/DDP leg
+        # needs NCCL and is skipped then
         if os.environ.get("LGN_BENCH_BACKEND", "nccl") == "gloo":
             dist.init_process_group("gloo")
             args.no_train_epoch = True
@@ -334,17 +412,14 @@ def run_b200(args):
     cfg = workload(args)
     N, D, B, fanout = cfg["n_nodes"], cfg["dim"], cfg["batch"], cfg["fanout"]
     rng_mode = L.RNG_PHILOX if args.rng == "philox" else L.RNG_MINSTD
-    early_shard = None
-    if os.environ.get("LGN_BENCH_EARLY_SHARD") and world > 1 and args.placement == "sharded":
-        # experiment: reserve the feature shard before anything else is allocated on the device
-        from legion_b200 import cluster as _cl
-        early_shard = L.DevArray.zeros((_cl.capacity_for(int(N * args.cache_frac), world), D), np.float32)
+    row_bytes = 4 * D
+    t_start = time.perf_counter()
 
     # ---- dataset, resident in HBM before the timed region --------------------------------
     dmin = L.synth.calibrate_dmin(cfg["avg_deg"], N)
     ds = L.synth.make_dataset(N, cfg["avg_deg"], D, n_class=cfg["n_class"], backend="torch", device=dev, dmin_fp=dmin)
     torch.cuda.synchronize()
-    from legion_b200 import cluster
+    t_dataset = time.perf_counter() - t_start
     my_train = cluster.partition_seeds(ds.train_ids, world, rank).contiguous()        # GPUGraphStore.cu:338
     my_labels = ds.labels[my_train.long()].contiguous()
     train_steps = cluster.train_steps(my_train.numel(), B, dist if world > 1 else None)    # CUDA_IPC_Service.cu:88
@@ -352,15 +427,21 @@ def run_b200(args):
     r = L.Runner(N, D, B, fanout, device=local, part=rank, rng_mode=rng_mode, rng_seed=42, enable_hotness=True, n_lanes=args.lanes)
     r.bind_topology(ds.indptr, ds.indices)            # topology replicated in HBM (7 % of one B200 even for papers100M)
     r.bind_seeds(L.MODE_TRAIN, my_train, my_labels)
-    # one sampling stream per pipeline slot (two independent lanes, PIPELINE_DEPTH 2) + a consumer-side stream
     NL = args.lanes
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]     # one sampling stream per batch slot
     lp = [x.cuda_stream for x in lanes]
     stream, sp = lanes[0], lp[0]
     stream2 = torch.cuda.Stream(device=dev)       # consumer-side stream of the e2e leg (result read-back)
     sp2 = stream2.cuda_stream
 
-    # ---- presampling epoch -> hotness -> (allreduce) -> hot order -> shards ---------------
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- presampling epoch (epoch 0) -> hotness -> all-reduce -> hot order -----------------
+    r.set_epoch(0)
     t_pre = time.perf_counter()
     for step in range(train_steps):
         r.batch_generate(L.MODE_TRAIN, B, step, stream=lp[step % NL], pipe=step % NL)
@@ -369,7 +450,7 @@ def run_b200(args):
     t_pre = time.perf_counter() - t_pre
     r.set_dedup_capacity(max(1, r.max_ids()))     # hash dedup table: 2.5 x the largest presampled batch (no-op for the direct map)
     nh, _th = r.hotness()
-    if world > 1:   # the path's one collective: NCCL all-reduce of the hotness histogram (replaces aggregate_access)
+    if world > 1:   # the path's one collective: all-reduce of the hotness histogram (replaces aggregate_access, GPUCache.cu:624-647)
         how = os.environ.get("LGN_BENCH_HOTNESS", "nccl" if dist.get_backend() == "nccl" else "host")
         nh_t = torch.as_tensor(cluster._DeviceView(nh.ptr, N), device=dev)
         if how == "none":       # diagnostic: no reduction at all, identical (id-ordered) placement on every rank
@@ -384,111 +465,173 @@ def run_b200(args):
         torch.cuda.synchronize()
     order = L.hot_order(nh)
     kg = world
-    row_bytes_ = 4 * D
     n_cached = int(N * args.cache_frac)
-    budget_rows = int(args.gpu_cache_gb * 1e9 // row_bytes_)
-    if args.placement == "replicated" or kg == 1:
-        n_repl = min(n_cached, budget_rows) if args.placement == "replicated" else 0
-    elif args.placement == "hybrid":      # replicate as many of the hottest rows as the budget allows, partition the rest
-        n_repl = max(0, min(n_cached, (budget_rows * kg - n_cached) // (kg - 1)))
-    else:
-        n_repl = 0
-    if args.placement == "replicated":
-        cap = max(1, n_repl)
-    else:
-        cap = n_repl + cluster.capacity_for(n_cached - n_repl, kg)
-    if kg > 1 and n_repl >= n_cached:      # nothing is partitioned: every GPU holds the whole cached set, no peer shards to bind
-        kg_bind, part_bind = 1, 0
-    else:
-        kg_bind, part_bind = kg, rank
-    r.set_part(part_bind)
-    slot_of = L.place_hybrid(order, cap, kg_bind, n_repl, part_bind)
-    base = ds.features
-    host_tier = None
-    if args.cache_frac < 1.0 or (args.placement == "replicated" and n_repl < N):   # misses: pinned host memory over UVA
-        host_tier = L.MappedHostArray((N, D), np.float32)
-        torch.from_numpy(host_tier.array).copy_(ds.features.cpu())
-        base = host_tier
-    r.bind_features(base)
-    if early_shard is not None and early_shard.shape != (cap, D):
-        early_shard = None
-    # LGN_BENCH_SHARD_ALLOC=vmm: shards created with the VMM API and shared as file descriptors (lgn_shared_*) instead
-    # of cudaMalloc + legacy CUDA IPC handles (diagnostic alternative for the NVLink tier)
-    use_vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm" and kg_bind > 1
-    shard_fd = mapped_bytes = None
-    if use_vmm:
-        early_shard, shard_fd, mapped_bytes = L.shared_alloc((cap, D), np.float32)
-    my_shard = L.fill_feature_shard_hybrid(order, cap, kg_bind, part_bind, n_repl, ds.features, D, out=early_shard)
-    shards = [my_shard]
-    imported = []
-    if kg_bind > 1 and use_vmm:
-        torch.cuda.synchronize()
-        fds = cluster.exchange_fds(dist, shard_fd)
-        sizes = [None] * world
-        dist.all_gather_object(sizes, int(mapped_bytes))
-        shards = []
-        for j in range(world):
-            if j == rank:
-                shards.append(my_shard)
-            else:
-                shards.append(L.shared_import(fds[j], sizes[j], (cap, D), np.float32))
-                os.close(fds[j])
-        os.close(shard_fd)
-    elif kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
-        import ctypes as C
-        h = (C.c_uint8 * 64)()
-        L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(my_shard.ptr), h), "ipc_export")
-        handles = cluster.exchange_handles(dist, bytes(h))
-        shards = []
-        for j in range(world):
-            if j == rank:
-                shards.append(my_shard)
-                continue
-            p = C.c_void_p()
-            hb = (C.c_uint8 * 64).from_buffer_copy(handles[j])
-            L._lib.check(L.lib().lgn_ipc_import(hb, C.byref(p)), "ipc_import")
-            imported.append(p)
-            shards.append(L.DevArray((cap, D), np.float32, ptr=p.value, owner=False))
-    r.bind_feature_cache(shards, slot_of, cap)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    peer_debug = None
-    if os.environ.get("LGN_BENCH_PEER_DEBUG") and kg_bind > 1:
-        # diagnostic (NVLink tier): the probe's plain LDG loop over THIS process's shard mappings,
-        # all ranks at once, before anything else runs: uniform rows over the whole shard and over its first 64 Ki rows
-        peer_debug = {}
-        n_dbg = min(200_000, r.capacity)
-        for tag, rows in (("whole_shard", cap), ("first_64Ki_rows", min(cap, 65536))):
-            dist.barrier()
-            ms_dbg = r.debug_shard_read(n_dbg, rows, peers_only=True, repeats=6, stream=lp[0])
-            peer_debug[tag + "_GBps"] = n_dbg * 4 * D / (ms_dbg / 1e3) / 1e9
-        sys.stderr.write("rank %d peer_debug %s\n" % (rank, peer_debug))
-        dist.barrier()
+    budget_gb = args.gpu_cache_gb if args.gpu_cache_gb > 0 else (38.0 if world > 1 else N * row_bytes / 1e9 + 1.0)
+    budget_rows = int(budget_gb * 1e9 // row_bytes)
 
-    # ---- the timed step -------------------------------------------------------------------
+    # ---- link probes for the hit-mix roofline (measured, not nominal) ----
+    def copy_GBps(dst, src, nbytes, reps=4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        L._lib.check(L.lib().lgn_copy_async(C.c_void_p(dst), C.c_void_p(src), C.c_int64(nbytes), C.c_void_p(sp)), "copy")
+        e0.record(stream)
+        for _ in range(reps):
+            L._lib.check(L.lib().lgn_copy_async(C.c_void_p(dst), C.c_void_p(src), C.c_int64(nbytes), C.c_void_p(sp)), "copy")
+        e1.record(stream)
+        e1.synchronize()
+        return nbytes * reps / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+    probe_bytes = 256 << 20
+    pin = L.MappedHostArray((probe_bytes // 4,), np.float32)
+    scratch = L.DevArray((probe_bytes // 4,), np.float32)
+    pin.array[:] = 1.0
+    pcie_h2d = copy_GBps(scratch.ptr, pin.host_ptr, probe_bytes)
+    pcie_d2h = copy_GBps(pin.host_ptr, scratch.ptr, probe_bytes)
+    pin.free()
+
+    # ---- cache placements ------------------------------------------------------------------
+    host_tier = [None]
+
+    def build_cache(placement):
+        c = Cache()
+        c.placement = placement
+        if placement == "replicated" or kg == 1:
+            c.n_repl = min(n_cached, budget_rows) if placement == "replicated" else 0
+        elif placement == "hybrid":      # replicate as many of the hottest rows as the budget allows, partition the rest
+            c.n_repl = max(0, min(n_cached, (budget_rows * kg - n_cached) // (kg - 1)))
+        else:
+            c.n_repl = 0
+        if placement == "replicated":
+            c.cap = max(1, c.n_repl)
+        else:
+            part_rows = min(n_cached - c.n_repl, max(0, budget_rows - c.n_repl) * kg)
+            c.cap = c.n_repl + cluster.capacity_for(part_rows, kg)
+        if kg > 1 and c.n_repl >= n_cached:      # nothing is partitioned: every GPU holds the whole cached set, no peer shards to bind
+            c.kg_bind, part_bind = 1, 0
+        else:
+            c.kg_bind, part_bind = kg, rank
+        r.set_part(part_bind)
+        c.slot_of = L.place_hybrid(order, c.cap, c.kg_bind, c.n_repl, part_bind)
+        base = ds.features
+        cached_rows = c.n_repl + (c.cap - c.n_repl) * c.kg_bind
+        if cached_rows < N:       # misses: pinned host memory over UVA (only then is the 4*N*D-byte host copy made)
+            if host_tier[0] is None:
+                host_tier[0] = L.MappedHostArray((N, D), np.float32)
+                rows = max(1, (1 << 28) // row_bytes)
+                for lo in range(0, N, rows):
+                    host_tier[0].array[lo:lo + rows] = ds.features[lo:lo + rows].cpu().numpy()
+            base = host_tier[0]
+        r.bind_features(base)
+        c.vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm" and c.kg_bind > 1
+        shard_fd = mapped_bytes = None
+        out = None
+        if c.vmm:
+            out, shard_fd, mapped_bytes = L.shared_alloc((c.cap, D), np.float32)
+        c.my_shard = L.fill_feature_shard_hybrid(order, c.cap, c.kg_bind, part_bind, c.n_repl, ds.features, D, out=out)
+        c.shards = [c.my_shard]
+        if c.kg_bind > 1 and c.vmm:
+            torch.cuda.synchronize()
+            fds = cluster.exchange_fds(dist, shard_fd)
+            sizes = [None] * world
+            dist.all_gather_object(sizes, int(mapped_bytes))
+            c.shards = []
+            for j in range(world):
+                if j == rank:
+                    c.shards.append(c.my_shard)
+                else:
+                    a = L.shared_import(fds[j], sizes[j], (c.cap, D), np.float32)
+                    c.imported.append(a)
+                    c.shards.append(a)
+                    os.close(fds[j])
+            os.close(shard_fd)
+        elif c.kg_bind > 1:   # peer shards: CUDA IPC handles exchanged once, then plain P2P loads inside the gather kernel
+            torch.cuda.synchronize()
+            h = (C.c_uint8 * 64)()
+            L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(c.my_shard.ptr), h), "ipc_export")
+            handles = cluster.exchange_handles(dist, bytes(h))
+            c.shards = []
+            for j in range(world):
+                if j == rank:
+                    c.shards.append(c.my_shard)
+                    continue
+                p = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(handles[j])
+                L._lib.check(L.lib().lgn_ipc_import(hb, C.byref(p)), "ipc_import")
+                c.imported.append(p)
+                c.shards.append(L.DevArray((c.cap, D), np.float32, ptr=p.value, owner=False))
+        r.bind_feature_cache(c.shards, c.slot_of, c.cap)
+        barrier()
+        return c
+
+    def drop_cache(c):
+        barrier()
+        for p in c.imported:
+            if c.vmm:
+                L.shared_free(p)
+            else:
+                L.lib().lgn_ipc_close(p)
+        barrier()                      # every importer has unmapped before any owner frees
+        if c.vmm:
+            L.shared_free(c.my_shard)
+        else:
+            c.my_shard.free()
+        c.slot_of.free()
+        c.shards, c.imported = [], []
+
+    # ---- parity: one mini-batch of THIS rank against the CPU oracle, through the real tier mappings ----
+    oracle_state = {}
+
+    def parity_check(c, step=0, epoch=1):
+        from oracle import oracle as O
+        if "smp" not in oracle_state:
+            oracle_state["smp"] = O.Sampler(ds.indptr.cpu().numpy(), ds.indices.cpu().numpy(), fanout,
+                                            rng_mode=O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD, rng_seed=42,
+                                            n_threads=max(1, (os.cpu_count() or 8) // max(1, world)))
+        seeds = my_train[step * B:(step + 1) * B].cpu().numpy()
+        labels = my_labels[step * B:(step + 1) * B].cpu().numpy()
+        if "want" not in oracle_state:
+            oracle_state["want"] = oracle_state["smp"].sample(seeds, step=step, epoch=epoch)
+        want = oracle_state["want"]
+        r.set_epoch(epoch)
+        r.batch_from_host(seeds, labels, step=step, stream=sp, pipe=0)
+        r.run_batch(with_features=True, stream=sp)
+        got = r.fetch(with_features=True, stream=sp)
+        total, n_e = int(want["nc"][0]), int(want["ec"][0])
+        ok = np.array_equal(got["nc"], want["nc"]) and np.array_equal(got["ec"], want["ec"])
+        ok = ok and np.array_equal(got["sampled_ids"], want["sampled_ids"][:total])
+        for k in ("agg_src_ids", "agg_dst_ids", "agg_src_off", "agg_dst_off"):
+            ok = ok and np.array_equal(got[k], want[k][:n_e])
+        ok = ok and np.array_equal(got["labels"], labels)
+        if ok:       # features are closed-form (synth.features_block): every gathered row must equal its node's row, bit for bit
+            ids = want["sampled_ids"][:total].astype(np.uint64)
+            exp = ((ids[:, None] * np.uint64(2654435761) + np.arange(D, dtype=np.uint64)[None, :] * np.uint64(40503)) & np.uint64(0x7FFFFF)) \
+                + np.uint64(0x3F000000)
+            ok = np.array_equal(got["features"].view(np.uint32), exp.astype(np.uint32))
+        flag = torch.tensor([1 if ok else 0], device=rdev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            raise SystemExit(f"rank {rank}: mini-batch differs from the CPU oracle (placement {c.placement}, own result {'ok' if ok else 'WRONG'}) "
+                             "-- refusing to time a wrong result")
+        return {"rows": total, "edges": n_e}
+
+    # ---- measurement of one placement ------------------------------------------------------
     def step_resident(i):
         r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % NL], pipe=i % NL)
         r.run_batch(with_features=True, stream=lp[i % NL])
 
-    seeds_pin = torch.empty((train_steps, B), dtype=torch.int32).pin_memory()
-    labels_pin = torch.empty((train_steps, B), dtype=torch.int32).pin_memory()
-    seeds_pin.copy_(my_train[:train_steps * B].view(train_steps, B).cpu())
-    labels_pin.copy_(my_labels[:train_steps * B].view(train_steps, B).cpu())
+    n_pin = min(train_steps, max(64, args.steps + args.warmup + 8))
+    seeds_pin = torch.empty((n_pin, B), dtype=torch.int32).pin_memory()
+    labels_pin = torch.empty((n_pin, B), dtype=torch.int32).pin_memory()
+    seeds_pin.copy_(my_train[:n_pin * B].view(n_pin, B).cpu())
+    labels_pin.copy_(my_labels[:n_pin * B].view(n_pin, B).cpu())
 
     def step_e2e(i):
-        # double-buffered consumer (PIPELINE_DEPTH 2, like the reference's trainer handshake): enqueue batch i from
-        # pinned host seeds (H2D), then read batch i-1's result block (D2H + host sync) while batch i is in flight
-        j = i % train_steps
+        # double-buffered consumer (like the reference's trainer handshake): enqueue batch i from pinned host seeds (H2D),
+        # then read the oldest in-flight batch's result block (D2H + host sync)
+        j = i % n_pin
         r.batch_from_host(seeds_pin[j], labels_pin[j], step=j, stream=lp[i % NL], pipe=i % NL)
         r.run_batch(with_features=True, stream=lp[i % NL])
-        return r.read_counters(stream=sp2, pipe=(i + 1) % NL)          # oldest batch in flight
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        return r.read_counters(stream=sp2, pipe=(i + 1) % NL)
 
     host_ms = [0.0]
 
@@ -529,67 +672,81 @@ def run_b200(args):
         return float(t.item()), prof
 
     K, W = args.steps, max(args.warmup, 3)
+    hbm_peak, peak_src = peaks()
+
+    def count_work(K, W):
+        """work done in the timed steps (deterministic: replay the same steps untimed and read the counters)."""
+        edges = rows = 0
+        hop_items, hop_edges, hop_new = (np.zeros(len(fanout), np.int64) for _ in range(3))
+        for i in range(W, W + K):
+            step_resident(i)
+            nc, ec = r.read_counters(stream=sp)
+            edges += int(ec[0]); rows += int(nc[0])
+            prev_e = prev_items = 0
+            for h in range(len(fanout)):
+                e_h = int(ec[3 + h]) - prev_e
+                hop_items[h] += B if h == 0 else prev_items
+                hop_edges[h] += e_h; hop_new[h] += int(nc[6 + 2 * h])
+                prev_items, prev_e = e_h, int(ec[3 + h])
+        assert r.status(stream=sp) == 0, "device-side capacity overflow"
+        return edges, rows, hop_items, hop_edges, hop_new
+
+    def nvlink_probe(c):
+        """peer copy rate of THIS box: every rank copies 256 MB out of its right neighbour's shard at the same time."""
+        if c.kg_bind < 2:
+            return None
+        nb = min(probe_bytes, c.cap * row_bytes)
+        barrier()
+        g = copy_GBps(scratch.ptr, c.shards[(rank + 1) % world].ptr, nb)
+        t = torch.tensor([g], device=rdev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def hit_mix(tiers, rows, ms, nvl):
+        tsum = max(1, sum(tiers))
+        h_local, h_peer, h_host = tiers[0] / tsum, tiers[1] / tsum, tiers[2] / tsum
+        inv = h_local / (hbm_peak / 2) + h_peer / nvl + h_host / pcie_h2d
+        roof = 1.0 / inv if inv > 0 else hbm_peak / 2          # payload GB/s per GPU (BASELINE.md section 2)
+        inv_nom = h_local / (hbm_peak / 2) + h_peer / NVLINK_NOMINAL + h_host / pcie_h2d
+        payload = rows * row_bytes / (ms / 1e3) / 1e9
+        return {"local": h_local, "peer": h_peer, "host": h_host, "payload_roof_GBps_per_gpu": roof,
+                "achieved_payload_GBps_per_gpu": payload, "frac": payload / roof,
+                "frac_vs_nominal_900": payload * inv_nom,
+                "peaks_GBps": {"hbm_copy": hbm_peak, "nvlink_peer_copy_measured": nvl, "nvlink_nominal": NVLINK_NOMINAL,
+                               "pcie_h2d_pinned_measured": pcie_h2d, "pcie_d2h_pinned_measured": pcie_d2h},
+                "note": "achieved = feature payload of this rank's step / step time (sampling included); roof = 1 / (h_local/(HBM copy/2) + "
+                        "h_peer/NVLink + h_host/PCIe) with the link rates measured on this box"}
+
+    def measure_light(c):
+        """the graph-replayed timed region only (second placement)."""
+        r.set_epoch(1)
+        r.tier_counts(reset=True, stream=sp)
+        ms_total, _ = timed(step_resident, K, W)
+        tiers = r.tier_counts(reset=True, stream=sp)
+        edges, rows, *_ = count_work(K, W)
+        r.tier_counts(reset=True, stream=sp)
+        tot = torch.tensor([edges, rows], device=rdev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)
+        nvl = nvlink_probe(c) or 770.0
+        return {"placement": c.placement, "rows_replicated": int(c.n_repl), "rows_per_shard": int(c.cap),
+                "value": float(tot[0].item()) / (ms_total / 1e3), "unit": UNIT, "ms_per_step": ms_total / K,
+                "feature_extract_GBps": float(tot[1].item()) * row_bytes / (ms_total / 1e3) / 1e9,
+                "tier_rows_per_timed_region": [int(t * K / (K + W)) for t in tiers],
+                "hit_mix": hit_mix(tiers, rows, ms_total, nvl)}
+
     if args.probe:
-        def ev_time(fn, n):
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            fn(n)
-            for q in range(NL):
-                r.wait_pipe(q, stream=sp)
-            for x in lanes[1:]:
-                stream.wait_stream(x)
-            b.record(stream)
-            barrier()
-            return a.elapsed_time(b) / n
-        for nl in (1, 2, 4, 8):
-            if nl > NL:
-                break
-            def samp(n, nl=nl):
-                for i in range(n):
-                    r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % nl], pipe=i % nl)
-                    r.run_batch(with_features=False, stream=lp[i % nl])
-            samp(8); print(f"sampling only, {nl} lanes: {ev_time(samp, 40):.4f} ms/step", file=sys.stderr)
-        for nl in (1, 2, 4):
-            if nl > NL:
-                break
-            for q in range(nl):     # one sampled batch per lane, then gathers only
-                r.batch_generate(L.MODE_TRAIN, B, q, stream=lp[q], pipe=q)
-                r.run_batch(with_features=False, stream=lp[q])
-            def gath(n, nl=nl):
-                for i in range(n):
-                    r.pipe = i % nl
-                    L.lib().lgn_batch_buffers  # noqa
-                    r.select_pipe(i % nl)
-                    for seg in range(len(fanout) + 1):
-                        r.gather_segment(seg, stream=lp[i % nl])
-            gath(4); print(f"gather only, {nl} streams: {ev_time(gath, 40):.4f} ms/batch", file=sys.stderr)
-        def both(n):
-            for i in range(n):
-                step_resident(i)
-        both(8); print(f"full pipeline, {NL} lanes: {ev_time(both, 40):.4f} ms/step", file=sys.stderr)
-        if os.environ.get("LGN_NCU_RANGE"):       # ncu --replay-mode app-range: whole-range metrics under real concurrency
-            def samp4(n):
-                for i in range(n):
-                    r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % NL], pipe=i % NL)
-                    r.run_batch(with_features=False, stream=lp[i % NL])
-            fn = samp4 if os.environ["LGN_NCU_RANGE"] == "samp" else both
-            fn(8)
-            barrier()
-            torch.cuda.profiler.start()
-            fn(40)
-            barrier()
-            torch.cuda.profiler.stop()
-            return
-        both(NL * 2)
-        barrier()
-        r.profile_enable(1024)
-        both(NL * 3)
-        barrier()
-        names = {0: "begin", 1: "sample", 2: "gather", 3: "end"}
-        for kind, pipe, a, b in r.profile_timeline():
-            print(f"lane {pipe} {names[kind]:7s} {1e3 * a:9.1f} -> {1e3 * b:9.1f} us  ({1e3 * (b - a):7.1f})", file=sys.stderr)
-        return
+        c = build_cache(args.placement)
+        return probe_mode(L, r, dist, world, rank, c, lp, lanes, stream, sp, NL, B, D, train_steps, barrier, step_resident)
+
+    # ======================= primary placement ==============================================
+    c = build_cache(args.placement)
+    parity = None
+    if not args.no_parity:
+        t0 = time.perf_counter()
+        parity = parity_check(c)
+        parity["seconds"] = time.perf_counter() - t0
+    r.set_epoch(1)                                    # the timed epoch is not the presampled one
     clocks = ClockSampler(local)
     r.tier_counts(reset=True, stream=sp)
     clocks.start()
@@ -600,36 +757,23 @@ def run_b200(args):
     host_enqueue_plain_ms = host_ms[0]
     ms_e2e, _ = timed(step_e2e, K, W)
     clk = clocks.stop()                               # nvidia-smi samples span the three timed passes (each only a few ms long)
-
-    # work done in the timed steps (deterministic: replay the same steps untimed and read the counters)
-    edges = rows = 0
-    seg_rows = np.zeros(len(fanout) + 1, np.int64)
-    hop_items, hop_edges, hop_new = np.zeros(len(fanout), np.int64), np.zeros(len(fanout), np.int64), np.zeros(len(fanout), np.int64)
-    for i in range(W, W + K):
-        step_resident(i)
-        nc, ec = r.read_counters(stream=sp)
-        edges += int(ec[0]); rows += int(nc[0])
-        prev_e = 0
-        for h in range(len(fanout) + 1):
-            seg_rows[h] += int(nc[4 + 2 * h])
-        for h in range(len(fanout)):
-            e_h = int(ec[3 + h]) - prev_e
-            hop_items[h] += B if h == 0 else hop_edges_prev
-            hop_edges[h] += e_h; hop_new[h] += int(nc[6 + 2 * h])
-            hop_edges_prev, prev_e = e_h, int(ec[3 + h])
-    assert r.status(stream=sp) == 0, "device-side capacity overflow"
+    edges, rows, hop_items, hop_edges, hop_new = count_work(K, W)
     tot = torch.tensor([edges, rows], device=rdev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot)
     job_edges, job_rows = float(tot[0].item()), float(tot[1].item())
-
     value = job_edges / (ms_total / 1e3)
     e2e_value = job_edges / (ms_e2e / 1e3)
-    row_bytes = 4 * D
     feat_gbps = job_rows * row_bytes / (ms_total / 1e3) / 1e9
+    nvl = nvlink_probe(c) or 770.0
 
-    # ---- the dominant kernel timed ALONE (no other batch in flight): K batches are sampled first, then only their
-    # feature-extraction launches are replayed back to back on one stream between CUDA events
+    # long run of the same region: DVFS / pipeline-fill effects that 50 steps cannot show
+    long_K = int(os.environ.get("LGN_BENCH_LONG_STEPS", "2000"))
+    ms_long = None
+    if long_K > 0:
+        ms_long, _ = timed(step_resident, long_K, W)
+
+    # ---- the dominant kernel timed ALONE (no other batch in flight) ------------------------
     alone_ms = alone_calls = alone_rows = 0
     for i in range(W, W + min(K, 16)):
         q = i % NL
@@ -639,43 +783,33 @@ def run_b200(args):
         barrier()
         r.select_pipe(q)
         r.profile_enable(8)
-        if len(fanout) >= 1:                 # the launches lgn_run_batch issues: seeds fused with hop 1, then one per further hop
-            r.gather_segments(0, 2, stream=lp[q])
-            for seg in range(2, len(fanout) + 1):
-                r.gather_segment(seg, stream=lp[q])
-        else:
-            r.gather_segment(0, stream=lp[q])
+        r.gather_all(stream=lp[q])           # the launches lgn_run_batch issues for the batch's feature extraction
         torch.cuda.synchronize()
         ms_k, calls_k = r.profile_collect()
         r.profile_enable(0)
         alone_ms += ms_k[2]; alone_calls += calls_k[2]; alone_rows += int(nc_[0])
 
     # ---- roofline of the dominant kernel (feature gather), timed live with CUDA events ----
-    hbm_peak, peak_src = peaks()
     ms_kind, calls, gather_busy_ms = prof
     gather_ms, gather_calls = ms_kind[2], calls[2]
     alg_bytes = rows * (2 * row_bytes + 8)                   # 2r + 8 per unique row (this rank)
-    # launches of different batches overlap in time (4 batches in flight): the denominator is the time during which at
-    # least one gather launch is executing (union of the launches' [begin, end] CUDA-event intervals), i.e. the average
-    # launch duration with overlap counted once; the plain sum of durations is kept as `per_launch_sum`
     achieved = alg_bytes / (gather_busy_ms / 1e3) / 1e9 if gather_busy_ms > 0 else 0.0
     achieved_sum = alg_bytes / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
     samp_bytes = float(sum(16 * hop_items[h] + 12 * hop_edges[h] + 4 * hop_new[h] for h in range(len(fanout))))
-    tsum = max(1, sum(tiers))
-    h_local, h_peer, h_host = tiers[0] / tsum, tiers[1] / tsum, tiers[2] / tsum
-    nvl, pcie = 770.0, 55.0                                  # measured peer copy (B200_PROFILING.md) / PCIe Gen5 x16 payload
-    inv = h_local / (hbm_peak / 2) + h_peer / nvl + h_host / pcie
-    hitmix_roof = 1.0 / inv if inv > 0 else hbm_peak / 2   # payload GB/s per GPU
-    gather_payload = rows * row_bytes / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
-    step_payload = rows * row_bytes / (ms_total / 1e3) / 1e9          # rows this GPU extracted per second of the whole pipeline
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01b_gather_traffic.json")
-    if os.path.exists(tp) and gather_calls:      # DRAM bytes per launch from the committed ncu --set full capture, scaled by rows
-        traffic = json.load(open(tp))["traffic_bytes_per_row"] * rows / gather_calls
-    kname = "k_gather_bulk (cp.async.bulk feature extraction)" if os.environ.get("LGN_GATHER", "bulk" if kg_bind == 1 else "ldg")[0] != "l" else "k_gather_v4 (128-bit LDG feature extraction)"
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+    traffic = wasted = None
+    tp = os.path.join(ROOT, "profiles", "r02_gather_traffic.json")
+    if os.path.exists(tp) and gather_calls:      # DRAM bytes per row from this round's ncu --set full capture of the same kernel
+        tj = json.load(open(tp)).get(args.config)
+        if tj:
+            traffic = tj["traffic_bytes_per_row"] * rows / gather_calls
+            wasted = tj["traffic_bytes_per_row"] / (2 * row_bytes + 8)
+    scale = (K + W) / K      # tiers were counted over warm-up + timed steps of the instrumented pass
+    roofline = {"bound": "hbm", "kernel": r.gather_kernel_name(), "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_over_algorithmic": wasted, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, gather_calls),
+                "step": {"achieved": alg_bytes / (ms_total / 1e3) / 1e9, "frac": alg_bytes / (ms_total / 1e3) / 1e9 / hbm_peak,
+                         "note": "the same algorithmic bytes over the WHOLE step time of the timed region (sampling included): what a reader "
+                                 "recomputes from rows x bytes / ms_per_step"},
                 "alone": {"achieved": alone_rows * (2 * row_bytes + 8) / (alone_ms / 1e3) / 1e9 if alone_ms else None,
                           "frac": alone_rows * (2 * row_bytes + 8) / (alone_ms / 1e3) / 1e9 / hbm_peak if alone_ms else None,
                           "launches": int(alone_calls), "avg_launch_us": 1e3 * alone_ms / max(1, alone_calls),
@@ -687,38 +821,41 @@ def run_b200(args):
                 "launches": int(gather_calls), "avg_launch_us": 1e3 * gather_busy_ms / max(1, gather_calls),
                 "per_launch_sum": {"achieved": achieved_sum, "frac": achieved_sum / hbm_peak, "avg_launch_us": 1e3 * gather_ms / max(1, gather_calls)},
                 "algorithmic_bytes_per_row": 2 * row_bytes + 8,
-                "hit_mix": {"local": h_local, "peer": h_peer, "host": h_host, "payload_roof_GBps_per_gpu": hitmix_roof,
-                            "achieved_payload_GBps_per_gpu": step_payload, "frac": step_payload / hitmix_roof,
-                            "per_launch_payload_GBps": gather_payload,
-                            "note": "achieved = feature payload of the step / step time (sampling included); per_launch = same bytes / summed launch durations, which overlap across the batches in flight"},
+                "hit_mix": hit_mix(tiers, rows * scale, ms_total * scale, nvl),
                 "sampler": {"ms_per_step": ms_kind[1] / K, "algorithmic_GBps": samp_bytes / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] else 0.0},
                 "share_of_step": {"gather_ms": gather_ms / K, "sample_ms": ms_kind[1] / K, "begin_ms": ms_kind[0] / K,
                                   "end_ms": ms_kind[3] / K, "step_ms": ms_prof / K,
                                   "note": "operator durations from the instrumented pass over the same K steps (per-operator CUDA events need eager launches, "
                                           "so that pass is a few % slower than the graph-replayed timed region); gather and sampling overlap on separate streams"}}
-
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
-            "config": {"workload": f"{args.config} {SHAPE_NAME.get(args.config, 'synthetic')}-shaped synthetic ({N} nodes, {ds.n_edges} edges, {D}-d), "
-                                   f"GraphSAGE fanout {fanout}, batch {B}/GPU, rng {args.rng}, cache_frac {args.cache_frac}, kg {kg}, placement {args.placement} ({n_repl} rows replicated), {NL} batches in flight",
-                       "parallelism": f"dp{world}: seeds tid%{world}, feature cache {args.placement} over {kg} GPU(s)",
-                       "l2": "working set (feature shard %.2f GB + 9.8 MB slot table + 0.26 GB CSR) larger than the 126 MB L2; "
-                             "consecutive steps touch different rows" % (cap * row_bytes / 1e9),
-                       "global_batch": B * world, "train_steps_per_epoch": train_steps},
+            "config": {"workload": workload_string(args, cfg, ds.n_edges),
+                       "parallelism": f"dp{world}: seeds tid%{world}, feature cache {c.placement} over {kg} GPU(s), topology replicated in HBM",
+                       "placement": c.placement, "rows_replicated": int(c.n_repl), "rows_per_shard": int(c.cap), "cache_frac": args.cache_frac,
+                       "gpu_cache_budget_GB": budget_gb, "batches_in_flight": NL,
+                       "l2": "inputs larger than L2: working set (feature shard %.2f GB + %.2f GB CSR) against 126 MB; "
+                             "consecutive steps touch different rows" % (c.cap * row_bytes / 1e9, (8 * N + 4 * ds.n_edges) / 1e9),
+                       "global_batch": B * world, "train_steps_per_epoch": train_steps,
+                       "timed_epoch": "epoch 1 (presampling saw epoch 0: other neighbourhoods)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 128,
                     "ms_per_step": ms_e2e / K,
-                    "note": "lgn_batch_from_host (pinned seeds+labels H2D) + lgn_run_batch + lgn_read_counters (D2H, sync) every step"},
-            "gpu_launches": int(K * (2 + 4 * len(fanout))),     # begin + (sample, mark, assign, gather) per hop + end, as CUDA-graph kernel nodes
+                    "note": "lgn_batch_from_host (pinned seeds+labels H2D) + lgn_run_batch + lgn_read_counters (D2H, sync) every step; "
+                            "extracted features stay in HBM for the on-GPU trainer, as in the reference"},
+            "gpu_launches": int(K * r.launches_per_batch()),
+            "parity_checked": parity is not None,
             "roofline": roofline,
             "extra": {"feature_extract_GBps": feat_gbps, "unique_rows_per_step": rows / K, "edges_per_step": edges / K,
                       "graphsage_dataloading_epoch_s": train_steps * ms_total / K / 1e3,
-                      "presampling_epoch_s": t_pre, "tier_rows": tiers,
+                      "presampling_epoch_s": t_pre, "dataset_build_s": t_dataset,
+                      "tier_rows_per_timed_region": [int(t / scale) for t in tiers],
                       "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_ms_per_step_unprofiled": host_enqueue_plain_ms,
-                      "ms_per_step_instrumented_pass": ms_prof / K}}
-    if peer_debug is not None:
-        line["extra"]["peer_debug"] = peer_debug
+                      "ms_per_step_instrumented_pass": ms_prof / K,
+                      "parity": parity and dict(parity, what="nc, ec, sampled_ids, 4 edge arrays, labels, features of batch 0 of epoch 1 of every rank "
+                                                            "== CPU oracle, bit for bit, read through the bound tier mappings")}}
+    if ms_long is not None:
+        line["extra"]["long_run"] = {"steps": long_K, "ms_per_step": ms_long / long_K}
 
     if not args.no_train_epoch:
         try:
@@ -726,22 +863,131 @@ def run_b200(args):
         except Exception as e:      # noqa: BLE001  (the model leg must never invalidate the data-path numbers)
             line["extra"]["graphsage_epoch_error"] = repr(e)[:200]
 
+    # ======================= the reference partition, real NVLink peer reads ================
+    if world > 1 and c.placement != "sharded" and not args.no_extra_sharded:
+        try:
+            drop_cache(c)
+            c = build_cache("sharded")
+            if not args.no_parity:
+                parity_check(c)
+            sh = measure_light(c)
+            sh["parity_checked"] = not args.no_parity
+            line["extra"]["sharded"] = sh
+        except SystemExit:
+            raise
+        except Exception as e:      # noqa: BLE001
+            line["extra"]["sharded"] = {"error": repr(e)[:300]}
+    if world > 1:
+        line["extra"]["peer_parity"] = "bit-exact" if not args.no_parity else "skipped"
+
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
-        hd = L.synth.Dataset(indptr=ds.indptr.cpu().numpy(), indices=ds.indices.cpu().numpy(), features=ds.features.cpu().numpy(),
-                             train_ids=my_train.cpu().numpy(), dim=D)
-        eps, gb, n, cores, dt = cpu_leg(hd, cfg, args.cpu_seconds, 100000, O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD, 42)
-        line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{n} batches of {B} seeds of the same workload in {dt:.1f} s (oracle, OpenMP)",
-                                "feature_extract_GBps": gb}
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:      # noqa: BLE001
+            avail = 1 << 62
+        need = N * row_bytes + 8 * N + 4 * ds.n_edges
+        if avail > 1.4 * need:
+            smp = oracle_state.get("smp")
+            hd = L.synth.Dataset(indptr=smp.indptr if smp else ds.indptr.cpu().numpy(), indices=smp.indices if smp else ds.indices.cpu().numpy(),
+                                 features=_chunked_to_host(ds.features, D), train_ids=my_train.cpu().numpy(), dim=D)
+            eps, gb, n, cores, dt = cpu_leg(hd, cfg, args.cpu_seconds, 100000, O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD, 42)
+            line["cpu_baseline"] = {"value": eps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} batches of {B} seeds of the same workload in {dt:.1f} s (oracle, OpenMP)",
+                                    "feature_extract_GBps": gb}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"skipped: host copy of the dataset needs {need / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}
+    line["extra"]["bench_wall_s"] = time.perf_counter() - t_start
     if rank == 0:
         emit(line)
-    for p in imported:
-        L.lib().lgn_ipc_close(p)
     if world > 1:
+        drop_cache(c)
         dist.barrier()
         dist.destroy_process_group()
+
+
+def probe_mode(L, r, dist, world, rank, c, lp, lanes, stream, sp, NL, B, D, train_steps, barrier, step_resident):
+    """debug: in-process shard read through the real peer mappings, then sampling-only / gather-only / full loops."""
+    import torch
+    r.set_epoch(1)
+    if os.environ.get("LGN_BENCH_PEER_DEBUG") and c.kg_bind > 1:
+        peer_debug = {}
+        n_dbg = min(200_000, r.capacity)
+        for tag, rows in (("whole_shard", c.cap), ("first_64Ki_rows", min(c.cap, 65536))):
+            dist.barrier()
+            ms_dbg = r.debug_shard_read(n_dbg, rows, peers_only=True, repeats=6, stream=lp[0])
+            peer_debug[tag + "_GBps"] = n_dbg * 4 * D / (ms_dbg / 1e3) / 1e9
+        log("rank %d peer_debug %s" % (rank, peer_debug))
+        dist.barrier()
+        if os.environ["LGN_BENCH_PEER_DEBUG"] == "exit":
+            return
+
+    def ev_time(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn(n)
+        for q in range(NL):
+            r.wait_pipe(q, stream=sp)
+        for x in lanes[1:]:
+            stream.wait_stream(x)
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / n
+    for nl in (1, 2, 4, 8):
+        if nl > NL:
+            break
+
+        def samp(n, nl=nl):
+            for i in range(n):
+                r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % nl], pipe=i % nl)
+                r.run_batch(with_features=False, stream=lp[i % nl])
+        samp(8)
+        log(f"rank {rank} sampling only, {nl} lanes: {ev_time(samp, 40):.4f} ms/step")
+    for nl in (1, 2, 4):
+        if nl > NL:
+            break
+        for q in range(nl):     # one sampled batch per lane, then gathers only
+            r.batch_generate(L.MODE_TRAIN, B, q, stream=lp[q], pipe=q)
+            r.run_batch(with_features=False, stream=lp[q])
+
+        def gath(n, nl=nl):
+            for i in range(n):
+                r.select_pipe(i % nl)
+                r.gather_all(stream=lp[i % nl])
+        gath(4)
+        log(f"rank {rank} gather only, {nl} streams: {ev_time(gath, 40):.4f} ms/batch")
+
+    def both(n):
+        for i in range(n):
+            step_resident(i)
+    both(8)
+    log(f"rank {rank} full pipeline, {NL} lanes: {ev_time(both, 40):.4f} ms/step")
+    if os.environ.get("LGN_NCU_RANGE"):       # ncu --replay-mode app-range: whole-range metrics under real concurrency
+        def samp4(n):
+            for i in range(n):
+                r.batch_generate(L.MODE_TRAIN, B, i % train_steps, stream=lp[i % NL], pipe=i % NL)
+                r.run_batch(with_features=False, stream=lp[i % NL])
+        fn = samp4 if os.environ["LGN_NCU_RANGE"] == "samp" else both
+        fn(8)
+        barrier()
+        torch.cuda.profiler.start()
+        fn(40)
+        barrier()
+        torch.cuda.profiler.stop()
+        return
+    both(NL * 2)
+    barrier()
+    r.profile_enable(1024)
+    both(NL * 3)
+    barrier()
+    if rank == 0:
+        names = {0: "begin", 1: "sample", 2: "gather", 3: "end"}
+        for kind, pipe, a, b in r.profile_timeline():
+            log(f"lane {pipe} {names[kind]:7s} {1e3 * a:9.1f} -> {1e3 * b:9.1f} us  ({1e3 * (b - a):7.1f})")
 
 
 def main():

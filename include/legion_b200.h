@@ -58,6 +58,7 @@ int lgn_copy_d2h(void* host_dst, const void* dev_src, int64_t bytes);
 int lgn_memset_d(void* dev_dst, int value, int64_t bytes);
 int lgn_copy_d2d(void* dev_dst, const void* dev_src, int64_t bytes);   /* any two devices (UVA) */
 int lgn_device_synchronize(void);
+int lgn_copy_async(void* dst, const void* src, int64_t bytes, void* stream);        /* any direction (UVA), on `stream` */
 /* streams for callers that do not link the CUDA runtime themselves (non-blocking; high_priority for sampling lanes) */
 int lgn_stream_create(void** stream, int32_t high_priority);
 int lgn_stream_destroy(void* stream);
@@ -109,6 +110,12 @@ int lgn_destroy(lgn_ctx* ctx);
  * number of unique ids per batch is known (lgn_max_ids); shrinking the table to ~2.5x that keeps it in L2.
  * Overflow is reported through lgn_status (LGN_E_CAPACITY), never silent.  No-op for the direct-map layout. */
 int lgn_set_dedup_capacity(lgn_ctx* ctx, int64_t expected_unique);
+/* Position of the following batches in the Philox stream (LGN_RNG_PHILOX only): counter = (slot, epoch, hop,
+ * step_offset + counter-or-step argument of lgn_batch_generate / lgn_batch_from_host), key = rng_seed.  A server
+ * passes the epoch of the global batch id and a per-mode offset (0 / train_step / train_step + valid_step) so that
+ * no two mini-batches of a run share a stream; the reference's minstd stream ignores both (it redraws the same
+ * neighbourhoods every epoch, Kernels.cu:402-405).  Defaults: 0, 0. */
+int lgn_set_epoch(lgn_ctx* ctx, uint32_t epoch, uint32_t step_offset);
 /* index of this GPU inside its NVLink clique, once the clique layout is known (PreSc's cache_agg_mode) */
 int lgn_set_part(lgn_ctx* ctx, int32_t part);
 /* B*(1+f1+f1*f2+...) : per-pipe id / edge buffer capacity (Server.cu:184-196). */
@@ -147,6 +154,12 @@ int lgn_sample_hop(lgn_ctx* ctx, void* stream, int32_t hop, int32_t is_presc);
 int lgn_gather_segment(lgn_ctx* ctx, void* stream, int32_t segment);
 /* n_segments adjacent segments in one launch (lgn_run_batch fuses the seeds with hop 1's new nodes) */
 int lgn_gather_segments(lgn_ctx* ctx, void* stream, int32_t first_segment, int32_t n_segments);
+/* every feature-extraction launch of the current slot's batch, exactly as lgn_run_batch issues them */
+int lgn_gather_batch(lgn_ctx* ctx, void* stream);
+/* kernels one lgn_batch_generate + lgn_run_batch pair launches (a caller's launch accounting) and the gather variant
+ * the bound tiers select */
+int32_t lgn_launches_per_batch(const lgn_ctx* ctx, int32_t with_features);
+const char* lgn_gather_kernel_name(const lgn_ctx* ctx);
 /* op 6/7: make_update_plan / update_cache (Kernels.cu:759-805): node hotness when
  * is_presc (HotnessMeasure, GPUCache.cu:227-235) and scratch reset (ClearPosMap). */
 int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);

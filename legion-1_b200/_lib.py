@@ -74,6 +74,8 @@ def lib():
         L.lgn_max_ids.restype = C.c_int32
         L.lgn_mode_of_step.restype = C.c_int32
         L.lgn_local_batch_id.restype = C.c_int32
+        L.lgn_launches_per_batch.restype = C.c_int32
+        L.lgn_gather_kernel_name.restype = C.c_char_p
         _lib = L
     return _lib
 

@@ -26,10 +26,10 @@ struct HopState {
 
 struct BatchState {
     HopState hop[LGN_MAX_HOPS + 1];
-    uint32_t step;          // philox counter word 3 (global batch id)
+    uint32_t step;          // philox counter word 3 (batch id inside the epoch, + the mode's offset)
     int32_t status;         // sticky: 0 or LGN_E_CAPACITY
     int32_t max_ids;        // max unique ids over presampled batches (GPUCache.cu:294-296)
-    int32_t pad;
+    uint32_t epoch;         // philox counter word 1
     unsigned long long tier_rows[4];   // local, peer, host rows gathered
     unsigned long long tot_items;      // frontier items expanded since the last reset (every hop)
     unsigned long long tot_edges;      // edges sampled since the last reset
@@ -206,7 +206,9 @@ __device__ __forceinline__ int32_t minstd_to_pick(uint32_t x, int32_t deg)
     return (int32_t)__dmul_rn(u, (double)deg);
 }
 
-// ---- Philox4x32-10, counter = (slot_lo, slot_hi, hop, step), key = seed ----
+// ---- Philox4x32-10, counter = (slot, epoch, hop, step), key = seed ----
+// A hop's slot index is < 2^30 (lgn_create bounds the capacity by CAND), so counter word 1 carries the epoch:
+// every (seed, epoch, step, hop, slot) draws from its own block; epoch 0 is the stream of round 1.
 __device__ __forceinline__ uint32_t philox_first_word(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                       uint32_t k0, uint32_t k1)
 {
@@ -220,10 +222,10 @@ __device__ __forceinline__ uint32_t philox_first_word(uint32_t c0, uint32_t c1, 
     }
     return c0;
 }
-__device__ __forceinline__ int32_t philox_pick(unsigned long long idx, uint32_t hop, uint32_t step,
+__device__ __forceinline__ int32_t philox_pick(unsigned long long idx, uint32_t epoch, uint32_t hop, uint32_t step,
                                                unsigned long long seed, int32_t deg)
 {
-    uint32_t r = philox_first_word((uint32_t)idx, (uint32_t)(idx >> 32), hop, step, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t r = philox_first_word((uint32_t)idx, epoch + (uint32_t)(idx >> 32), hop, step, (uint32_t)seed, (uint32_t)(seed >> 32));
     return (int32_t)__umulhi(r, (uint32_t)deg);
 }
 

@@ -297,6 +297,14 @@ public:
         st_.iter = env_->GetLocalBatchId(g);
         st_.batch_size = env_->GetCurrentBatchsize(dev_, st_.mode);
         st_.pipe = pipe_;
+        {   // Philox position: the epoch of the global batch id and a per-mode offset, so that no two mini-batches of a
+            // run share a stream (the reference's minstd stream redraws the same neighbourhoods every epoch)
+            const int per_epoch = env_->steps.train_step + env_->steps.valid_step;
+            const bool test = g >= per_epoch * env_->epochs;
+            const uint32_t epoch = test ? (uint32_t)env_->epochs : (uint32_t)(per_epoch > 0 ? g / per_epoch : 0);
+            const uint32_t off = st_.mode == LGN_MODE_TRAIN ? 0u : (st_.mode == LGN_MODE_VALID ? (uint32_t)env_->steps.train_step : (uint32_t)per_epoch);
+            LGN_DIE(lgn_set_epoch(st_.ctx, epoch + 1u, off), "lgn_set_epoch");      // epoch 0 is the presampling pass
+        }
         LGN_DIE(lgn_ipc_server_wait(env_->ipc, dev_, pipe_), "IPCWait");
         if (use_ops_) {
             for (int i = 0; i < op_num_; i++) {      // the reference's operator DAG, event-chained on two streams

@@ -26,6 +26,15 @@ int lgn_cuda_fail(cudaError_t e, const char* what)
 
 using namespace lgn;
 
+template <typename T>
+static cudaError_t malloc_pages(T** p, size_t n)
+{
+    const size_t page = (size_t)2 << 20;
+    if (n == 0) n = 1;
+    if (n >= page / 2) n = (n + page - 1) / page * page;
+    return cudaMalloc((void**)p, n);
+}
+
 extern "C" {
 
 const char* lgn_error_string(int code)
@@ -47,7 +56,17 @@ int lgn_version(void) { return 100; }
 int lgn_set_device(int32_t d) { CK(cudaSetDevice(d)); return LGN_OK; }
 int lgn_get_device(int32_t* d) { int x = 0; CK(cudaGetDevice(&x)); *d = x; return LGN_OK; }
 int lgn_device_count(int32_t* n) { int x = 0; CK(cudaGetDeviceCount(&x)); *n = x; return LGN_OK; }
-int lgn_device_alloc(void** p, int64_t bytes) { if (!p || bytes < 0) return LGN_E_ARG; CK(cudaMalloc(p, (size_t)(bytes > 0 ? bytes : 1))); return LGN_OK; }
+// Any allocation of this library may end up mapped by a peer (cache shards over cudaIpc* handles or direct P2P).  A
+// peer mapping of an allocation whose SIZE is not a multiple of the 2 MiB GPU page is built from small pages: random
+// 512-byte row reads over 7 x 2.56 GB of such mappings ran at 26 GB/s per GPU instead of 585 GB/s on 8xB200, the
+// translation misses stalling every other kernel on the GPU too (profiles/r02a_n8_collapse_diag_page_size.txt).
+// cudaMalloc hands out whole 2 MiB pages for large requests anyway, so rounding the request costs no memory.
+int lgn_device_alloc(void** p, int64_t bytes)
+{
+    if (!p || bytes < 0) return LGN_E_ARG;
+    CK(malloc_pages(p, (size_t)bytes));
+    return LGN_OK;
+}
 int lgn_device_free(void* p) { CK(cudaFree(p)); return LGN_OK; }
 int lgn_host_alloc_mapped(void** host, void** dev, int64_t bytes)
 {
@@ -62,6 +81,12 @@ int lgn_copy_d2h(void* h, const void* d, int64_t bytes) { CK(cudaMemcpy(h, d, (s
 int lgn_memset_d(void* d, int v, int64_t bytes) { CK(cudaMemset(d, v, (size_t)bytes)); return LGN_OK; }
 int lgn_copy_d2d(void* d, const void* s, int64_t bytes) { CK(cudaMemcpy(d, s, (size_t)bytes, cudaMemcpyDefault)); return LGN_OK; }
 int lgn_device_synchronize(void) { CK(cudaDeviceSynchronize()); return LGN_OK; }
+int lgn_copy_async(void* d, const void* s, int64_t bytes, void* stream)
+{
+    if (!d || !s || bytes < 0) return LGN_E_ARG;
+    CK(cudaMemcpyAsync(d, s, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return LGN_OK;
+}
 
 int lgn_stream_create(void** stream, int32_t high_priority)
 {
@@ -193,34 +218,34 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int p = 0; p < c->n_lanes; p++) {      // CUDA_IPC_Service.cu:140-215, Server.cu:217-231
         lgn::Pipe& pp = c->pipe[p];
-        CK(cudaMalloc(&pp.ids, cap * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.labels, (size_t)cfg->batch_size * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.agg_src_off, cap * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.agg_dst_off, cap * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.nc, 16 * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.ec, 16 * sizeof(int32_t)));
+        CK(malloc_pages(&pp.ids, cap * sizeof(int32_t)));
+        CK(malloc_pages(&pp.labels, (size_t)cfg->batch_size * sizeof(int32_t)));
+        CK(malloc_pages(&pp.agg_src_off, cap * sizeof(int32_t)));
+        CK(malloc_pages(&pp.agg_dst_off, cap * sizeof(int32_t)));
+        CK(malloc_pages(&pp.nc, 16 * sizeof(int32_t)));
+        CK(malloc_pages(&pp.ec, 16 * sizeof(int32_t)));
         CK(cudaMemset(pp.nc, 0, 64));
         CK(cudaMemset(pp.ec, 0, 64));
-        if (cfg->feat_dim > 0) CK(cudaMalloc(&pp.features, (size_t)c->max_rows * cfg->feat_dim * sizeof(float)));
+        if (cfg->feat_dim > 0) CK(malloc_pages(&pp.features, (size_t)c->max_rows * cfg->feat_dim * sizeof(float)));
         if (c->dedup_hash) {
             const size_t entries = (size_t)1 << c->dedup_bits_max;
-            CK(cudaMalloc(&pp.dedup_tab, entries * sizeof(unsigned long long)));
+            CK(malloc_pages(&pp.dedup_tab, entries * sizeof(unsigned long long)));
             CK(cudaMemset(pp.dedup_tab, 0xFF, entries * sizeof(unsigned long long)));
-            CK(cudaMalloc(&pp.slot_h, (max_slots + 16) * sizeof(int32_t)));
-            CK(cudaMalloc(&pp.id_h, cap * sizeof(int32_t)));
+            CK(malloc_pages(&pp.slot_h, (max_slots + 16) * sizeof(int32_t)));
+            CK(malloc_pages(&pp.id_h, cap * sizeof(int32_t)));
             pp.dedup.map = nullptr; pp.dedup.tab = pp.dedup_tab; pp.dedup.bits = c->dedup_bits_max;
         } else {
-            CK(cudaMalloc(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
+            CK(malloc_pages(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
             pp.dedup.map = pp.slot_map; pp.dedup.tab = nullptr; pp.dedup.bits = 0;
         }
-        CK(cudaMalloc(&pp.agg_src_ids, cap * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.agg_dst_ids, cap * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.slot_val, (max_slots + 16) * sizeof(int32_t)));
-        CK(cudaMalloc(&pp.tile_cnt, n_tiles * sizeof(unsigned long long)));
-        CK(cudaMalloc(&pp.state, sizeof(lgn::BatchState)));
+        CK(malloc_pages(&pp.agg_src_ids, cap * sizeof(int32_t)));
+        CK(malloc_pages(&pp.agg_dst_ids, cap * sizeof(int32_t)));
+        CK(malloc_pages(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
+        CK(malloc_pages(&pp.slot_val, (max_slots + 16) * sizeof(int32_t)));
+        CK(malloc_pages(&pp.tile_cnt, n_tiles * sizeof(unsigned long long)));
+        CK(malloc_pages(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
-        CK(cudaMalloc(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
+        CK(malloc_pages(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
         if (!c->dedup_hash) {
             int rc = fill_i32(pp.slot_map, lgn::EMPTY, cfg->n_nodes, 0);
             if (rc) return rc;
@@ -233,8 +258,8 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         CK(cudaEventCreateWithFlags(&pp.ev_join, cudaEventDisableTiming));
     }
     if (cfg->enable_hotness) {                                                   // GPUCache.cu:256-261 (u64 there)
-        CK(cudaMalloc(&c->node_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
-        CK(cudaMalloc(&c->topo_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+        CK(malloc_pages(&c->node_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
+        CK(malloc_pages(&c->topo_hotness, (size_t)cfg->n_nodes * sizeof(uint32_t)));
         CK(cudaMemset(c->node_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
         CK(cudaMemset(c->topo_hotness, 0, (size_t)cfg->n_nodes * sizeof(uint32_t)));
     }
@@ -307,6 +332,14 @@ int lgn_set_dedup_capacity(lgn_ctx* c, int64_t expected_unique)
     while (((long long)1 << bits) < (5 * expected_unique) / 2 && bits < c->dedup_bits_max) bits++;
     for (int i = 0; i < c->n_lanes; i++) c->pipe[i].dedup.bits = bits;
     invalidate_graphs(c);
+    return LGN_OK;
+}
+
+int lgn_set_epoch(lgn_ctx* c, uint32_t epoch, uint32_t step_offset)
+{
+    if (!c) return LGN_E_ARG;
+    c->rng_epoch = epoch;               // kernel arguments of the next k_batch_begin: no captured graph depends on them
+    c->rng_step_offset = step_offset;
     return LGN_OK;
 }
 
@@ -547,6 +580,36 @@ int lgn_gather_segments(lgn_ctx* c, void* stream, int32_t first, int32_t n)
     launch_gather(c, (cudaStream_t)stream, first, n);
     CK(cudaGetLastError());
     return LGN_OK;
+}
+
+// the feature-extraction launches of one batch, as lgn_run_batch issues them: the seeds are fused with hop 1's new
+// nodes (two small, latency-bound gathers become one), then one launch per further hop
+int lgn_gather_batch(lgn_ctx* c, void* stream)
+{
+    if (!c) return LGN_E_ARG;
+    if (!c->feat.base || c->cfg.feat_dim <= 0) return LGN_E_STATE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->cfg.n_hops == 0) return lgn_gather_segment(c, stream, 0);
+    for (int h = 0; h < c->cfg.n_hops; h++) {
+        ProfScope prof(c, s, 2);
+        if (h == 0) launch_gather(c, s, 0, 2); else launch_gather(c, s, h + 1, 1);
+        CK(cudaGetLastError());
+    }
+    return LGN_OK;
+}
+
+int32_t lgn_launches_per_batch(const lgn_ctx* c, int32_t with_features)
+{
+    if (!c) return 0;
+    const int hops = c->cfg.n_hops;
+    // k_batch_begin + (k_sample, k_mark, k_assign) per hop + k_batch_end, + the gathers of lgn_gather_batch
+    return 2 + 3 * hops + (with_features ? (hops == 0 ? 1 : hops) : 0);
+}
+
+const char* lgn_gather_kernel_name(const lgn_ctx* c)
+{
+    if (!c) return "";
+    return gather_kernel_name(c);
 }
 
 int lgn_finish_batch(lgn_ctx* c, void* stream, int32_t is_presc)

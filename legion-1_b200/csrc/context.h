@@ -93,6 +93,8 @@ struct lgn_ctx {
     int shared_gather_stream;  // 1: all slots' gathers run back to back on one stream (one saturates HBM already)
     int sample_ctas_per_sm, resolve_ctas_per_sm, end_ctas_per_sm;   // grid caps (CTAs per SM) of the persistent kernels
     int n_sm;
+    uint32_t rng_epoch;        // philox counter word 1 of the batches generated from now on (lgn_set_epoch)
+    uint32_t rng_step_offset;  // added to the batch counter to form philox counter word 3 (separates train/valid/test streams)
     // optional operator timing (lgn_profile_enable)
     cudaEvent_t* prof_ev;      // 2 events per record
     signed char* prof_kind;
@@ -109,6 +111,7 @@ void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
 // gather.cu
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs);
 void gather_init_device();
+const char* gather_kernel_name(const lgn_ctx* c);
 void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_rows, long long rows_per_shard, bool peers_only, uint32_t salt);
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,
                      float* dst, int n_sm, cudaStream_t s);

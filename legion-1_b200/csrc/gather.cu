@@ -275,13 +275,28 @@ void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_r
     k_debug_shard_read<<<c->n_sm * 3, GATHER_THREADS, 0, s>>>(tb, rows_per_shard, n_rows, c->cfg.feat_dim, c->pipe[pipe].features, salt);
 }
 
+static bool gather_vectorisable(const lgn_ctx* c, const Pipe& p)
+{
+    const int dim = c->cfg.feat_dim;
+    bool vec = (dim & 3) == 0 && ((uintptr_t)c->feat.base & 15) == 0 && ((uintptr_t)p.features & 15) == 0;
+    for (int i = 0; i < c->feat.n_parts; i++) vec = vec && ((uintptr_t)c->feat.shard_tab[i] & 15) == 0;
+    return vec;
+}
+
+const char* gather_kernel_name(const lgn_ctx* c)
+{
+    const Pipe& p = c->pipe[c->cur_pipe];
+    const int mode = c->gather_mode >= 0 ? c->gather_mode : (c->feat.n_parts > 1 ? 0 : 1);
+    if (!gather_vectorisable(c, p) || (c->cfg.feat_dim >> 2) > 128) return "k_gather_scalar";
+    return mode == 1 ? "k_gather_bulk (cp.async.bulk feature extraction)" : "k_gather_v4 (128-bit LDG feature extraction)";
+}
+
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
 {
     Pipe& p = c->pipe[c->cur_pipe];
     const int dim = c->cfg.feat_dim;
     const int seg_slot = 3 + 2 * segment;
-    bool vec = (dim & 3) == 0 && ((uintptr_t)c->feat.base & 15) == 0 && ((uintptr_t)p.features & 15) == 0;
-    for (int i = 0; i < c->feat.n_parts; i++) vec = vec && ((uintptr_t)c->feat.shard_tab[i] & 15) == 0;
+    const bool vec = gather_vectorisable(c, p);
     const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 8));   // grid-stride over 32-row chunks; < 8 CTAs/SM leaves room for the sampler
     FeatView fv = c->feat;
     const int nvec = dim >> 2;

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__
                                                      int32_t* __restrict__ ids, int32_t* __restrict__ labels,
                                                      const Dedup dd, int32_t* __restrict__ id_h, long long n_nodes,
                                                      int32_t* __restrict__ nc, int32_t* __restrict__ ec,
-                                                     BatchState* __restrict__ st, uint32_t step)
+                                                     BatchState* __restrict__ st, uint32_t step, uint32_t epoch)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsz = gridDim.x * blockDim.x;
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__
         HopState h0; h0.n_items = count; h0.item_base = 0; h0.node_base = count; h0.edge_base = 0;
         st->hop[0] = h0;
         st->step = step;
+        st->epoch = epoch;
     }
 }
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
     const int F = hs.n_items;
     const int t = threadIdx.x;
     const int32_t* frontier = hop == 0 ? ids : agg_src_ids + hs.item_base;   // Kernels.cu:368-374
-    const uint32_t step = st->step;
+    const uint32_t step = st->step, epoch = st->epoch;
     const unsigned long long keep = policy_evict_last();
 
     if (RNG == LGN_RNG_MINSTD)
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
                     if (RNG == LGN_RNG_MINSTD) {
                         pick = minstd_to_pick(mulmod_m31(s_pow[i], s_ak[k]), deg);
                     } else {
-                        pick = deg <= f ? k : philox_pick((unsigned long long)(slot0 + s), (uint32_t)hop, step, seed, deg);
+                        pick = deg <= f ? k : philox_pick((unsigned long long)(slot0 + s), epoch, (uint32_t)hop, step, seed, deg);
                     }
                     dst[u] = (int32_t)ld_nc_u32(s_base[i] + s_start[i] + pick);
                 }
@@ -412,10 +413,11 @@ void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const in
                         int32_t count, uint32_t step)
 {
     Pipe& p = c->pipe[c->cur_pipe];
+    step += c->rng_step_offset;
     int blocks = cdiv(count, 256);
     if (blocks < 1) blocks = 1;
     k_batch_begin<<<blocks, 256, 0, s>>>(ids + src_off, labels ? labels + src_off : nullptr, count, p.ids, p.labels,
-                                         p.dedup, p.id_h, c->cfg.n_nodes, p.nc, p.ec, p.state, step);
+                                         p.dedup, p.id_h, c->cfg.n_nodes, p.nc, p.ec, p.state, step, c->rng_epoch);
 }
 
 void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc)

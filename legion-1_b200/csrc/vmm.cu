@@ -10,6 +10,7 @@
 // loading on machines without libcuda.so.1 (the CPU test suite loads it to check the exported symbols).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -91,6 +92,18 @@ CUmemAllocationProp device_prop(int device)
     return prop;
 }
 
+// Size and address alignment of shared shards.  Random row reads out of multi-GB peer shards are bound by the
+// reach of the GPU's address translation, not by NVLink: physical size and virtual address
+// are therefore rounded to LGN_VMM_ALIGN_MB (default 512 MB, the largest GPU page) so the driver can map the shard
+// with its largest pages on the owner and on every importer.
+size_t huge_granularity(size_t gran)
+{
+    const char* e = getenv("LGN_VMM_ALIGN_MB");
+    size_t want = (size_t)(e ? atoll(e) : 512) << 20;
+    if (want < gran) want = gran;
+    return (want + gran - 1) / gran * gran;
+}
+
 // map `handle` (size bytes, already a multiple of the granularity) into this process and give `device` access
 int map_for_device(Driver* d, CUmemGenericAllocationHandle handle, size_t size, size_t gran, int device, void** out)
 {
@@ -139,6 +152,7 @@ int lgn_shared_alloc(void** dev_ptr, int64_t bytes, int32_t* fd_out, int64_t* ma
     size_t gran = 0, size = 0;
     int fd = -1;
     DRV(d->MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity");
+    gran = huge_granularity(gran);
     size = ((size_t)bytes + gran - 1) / gran * gran;
     DRV(d->MemCreate(&handle, size, &prop, 0), "cuMemCreate");
     created = true;
@@ -170,6 +184,7 @@ int lgn_shared_import(int32_t fd, int64_t mapped_bytes, void** dev_ptr)
     bool imported = false;
     size_t gran = 0;
     DRV(d->MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity");
+    gran = huge_granularity(gran);
     DRV(d->MemImportFromShareableHandle(&handle, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR), "cuMemImportFromShareableHandle");
     imported = true;
     rc = map_for_device(d, handle, (size_t)mapped_bytes, gran, device, dev_ptr);   // access is granted to THIS process's device

@@ -108,6 +108,16 @@ class Runner:
     def gather_segments(self, first, count, stream=None):
         check(lib().lgn_gather_segments(self.handle, _vp(stream), first, count), "lgn_gather_segments")
 
+    def gather_all(self, stream=None):
+        """every feature-extraction launch of the current slot's batch, as run_batch issues them."""
+        check(lib().lgn_gather_batch(self.handle, _vp(stream)), "lgn_gather_batch")
+
+    def launches_per_batch(self, with_features=True):
+        return int(lib().lgn_launches_per_batch(self.handle, int(with_features)))
+
+    def gather_kernel_name(self):
+        return lib().lgn_gather_kernel_name(self.handle).decode()
+
     def finish_batch(self, is_presc=False, stream=None):
         """Cache_Planner::run + Cache_Updater::run (Operator.cu:80-123)."""
         check(lib().lgn_finish_batch(self.handle, _vp(stream), int(is_presc)), "lgn_finish_batch")
@@ -115,6 +125,10 @@ class Runner:
     def run_batch(self, with_features=True, is_presc=False, stream=None):
         """GPURunner::RunOnce / RunPreSc minus the IPC handshake (Server.cu:284-328)."""
         check(lib().lgn_run_batch(self.handle, _vp(stream), int(with_features), int(is_presc)), "lgn_run_batch")
+
+    def set_epoch(self, epoch, step_offset=0):
+        """position of the following batches in the Philox stream (counter words 1 and 3)."""
+        check(lib().lgn_set_epoch(self.handle, C.c_uint32(epoch), C.c_uint32(step_offset)), "lgn_set_epoch")
 
     def set_part(self, part):
         check(lib().lgn_set_part(self.handle, C.c_int32(part)), "lgn_set_part")

@@ -65,9 +65,11 @@ void lgo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-int32_t lgo_philox_pick(uint64_t idx, uint32_t hop, uint32_t step, uint64_t seed, int32_t deg)
+int32_t lgo_philox_pick(uint64_t idx, uint32_t epoch, uint32_t hop, uint32_t step, uint64_t seed, int32_t deg)
 {
-    uint32_t ctr[4] = { (uint32_t)idx, (uint32_t)(idx >> 32), hop, step };
+    /* counter = (slot, epoch, hop, step): the slot index of a hop is < 2^30 (buffer capacity), so the word that
+     * used to carry its (always zero) high half carries the epoch -- epoch 0 is the round-1 stream */
+    uint32_t ctr[4] = { (uint32_t)idx, epoch + (uint32_t)(idx >> 32), hop, step };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     uint32_t out[4];
     lgo_philox4x32_10(ctr, key, out);
@@ -107,7 +109,7 @@ static inline int32_t draw(const lgo_sample_args* a, uint32_t hop, int32_t f, in
     if (a->rng_mode == LGO_RNG_MINSTD) return lgo_minstd_pick((uint64_t)idx, deg);
     /* philox mode: exact neighbourhood when the fanout covers the degree */
     if (deg <= f) return k;
-    return lgo_philox_pick((uint64_t)idx, hop, a->step, a->rng_seed, deg);
+    return lgo_philox_pick((uint64_t)idx, a->epoch, hop, a->step, a->rng_seed, deg);
 }
 
 int lgo_sample_batch(lgo_sample_args* a)
@@ -213,11 +215,11 @@ int lgo_sample_batch(lgo_sample_args* a)
 }
 
 void lgo_draw_hop(const int64_t* indptr, const int32_t* indices, const int32_t* frontier, int64_t n_items,
-                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, int32_t* out_dst)
+                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, uint32_t epoch, int32_t* out_dst)
 {
     lgo_sample_args a;
     memset(&a, 0, sizeof(a));
-    a.rng_mode = rng_mode; a.rng_seed = rng_seed; a.step = step;
+    a.rng_mode = rng_mode; a.rng_seed = rng_seed; a.step = step; a.epoch = epoch;
     for (int64_t idx = 0; idx < n_items * f; idx++) {
         int64_t i = idx / f; int32_t k = (int32_t)(idx % f);
         int32_t src = frontier[i], dst = -1;

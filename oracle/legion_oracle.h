@@ -39,9 +39,10 @@ uint32_t lgo_minstd_pow(uint64_t e);
 int32_t lgo_minstd_pick(uint64_t idx, int32_t deg);
 /* Philox4x32-10 (Salmon et al., SC'11), one block. */
 void lgo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* counter = (idx_lo, idx_hi, hop, step), key = (seed_lo, seed_hi);
- * pick = (out[0] * deg) >> 32. */
-int32_t lgo_philox_pick(uint64_t idx, uint32_t hop, uint32_t step, uint64_t seed, int32_t deg);
+/* counter = (slot, epoch, hop, step), key = (seed_lo, seed_hi); pick = (out[0] * deg) >> 32.
+ * slot = item*f + k inside the hop (< 2^30), epoch/step = position of the mini-batch in the run
+ * (stream keyed by seed, epoch, step, hop, slot). */
+int32_t lgo_philox_pick(uint64_t idx, uint32_t epoch, uint32_t hop, uint32_t step, uint64_t seed, int32_t deg);
 
 /* ---- batch generation (Kernels.cu:68-96, 163-232) --------------------- */
 /* Returns the actual number of seeds of step `counter` (Kernels.cu:224) and
@@ -62,7 +63,8 @@ typedef struct {
     const int32_t* fanout;   /* int32[n_hops] */
     int32_t rng_mode;        /* LGO_RNG_* */
     uint64_t rng_seed;       /* philox only */
-    uint32_t step;           /* philox only: global batch id */
+    uint32_t step;           /* philox only: batch id inside the epoch */
+    uint32_t epoch;          /* philox only: epoch (0 = first) */
     /* batch buffers, capacity entries each (labels not touched here) */
     int64_t capacity;
     int32_t n_seeds;         /* sampled_ids[0..n_seeds) already holds the seeds */
@@ -87,7 +89,7 @@ int lgo_sample_batch(lgo_sample_args* a);
  * out_dst[i*f+k] = sampled neighbour or -1.  Lets tests replay the reference's own (atomic-
  * arrival) frontier order, on which its hop>=2 draws depend through idx. */
 void lgo_draw_hop(const int64_t* indptr, const int32_t* indices, const int32_t* frontier, int64_t n_items,
-                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, int32_t* out_dst);
+                  int32_t f, int32_t rng_mode, uint64_t rng_seed, uint32_t hop, uint32_t step, uint32_t epoch, int32_t* out_dst);
 
 /* ---- cache planning (GPUCache.cu:578-659, 88-108, 200-205) ------------ */
 /* order[i] = node of rank i under (count desc, id asc). */

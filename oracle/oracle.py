@@ -35,7 +35,7 @@ def lib():
         _lib.lgo_minstd_pick.restype = C.c_int32
         _lib.lgo_minstd_pick.argtypes = [C.c_uint64, C.c_int32]
         _lib.lgo_philox_pick.restype = C.c_int32
-        _lib.lgo_philox_pick.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32]
+        _lib.lgo_philox_pick.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32]
         _lib.lgo_batch_generate.restype = C.c_int32
         _lib.lgo_fill_topo_shard.restype = C.c_int64
         _lib.lgo_mode_of_step.restype = C.c_int32
@@ -51,7 +51,7 @@ class SampleArgs(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p),
         ("n_hops", C.c_int32), ("fanout", C.c_void_p), ("rng_mode", C.c_int32),
-        ("rng_seed", C.c_uint64), ("step", C.c_uint32),
+        ("rng_seed", C.c_uint64), ("step", C.c_uint32), ("epoch", C.c_uint32),
         ("capacity", C.c_int64), ("n_seeds", C.c_int32),
         ("sampled_ids", C.c_void_p), ("agg_src_ids", C.c_void_p), ("agg_dst_ids", C.c_void_p),
         ("agg_src_off", C.c_void_p), ("agg_dst_off", C.c_void_p),
@@ -77,8 +77,9 @@ def philox4x32_10(ctr, key):
     return list(o)
 
 
-def philox_pick(idx, hop, step, seed, deg):
-    return lib().lgo_philox_pick(int(idx), int(hop), int(step), int(seed), int(deg))
+def philox_pick(idx, hop, step, seed, deg, epoch=0):
+    return lib().lgo_philox_pick(C.c_uint64(int(idx)), C.c_uint32(int(epoch)), C.c_uint32(int(hop)), C.c_uint32(int(step)),
+                                 C.c_uint64(int(seed)), C.c_int32(int(deg)))
 
 
 def capacity_for(batch, fanout):
@@ -116,7 +117,7 @@ class Sampler:
         self.topo_hotness = np.zeros(self.n, np.uint32)
         self.node_hotness = np.zeros(self.n, np.uint32)
 
-    def sample(self, seeds, step=0):
+    def sample(self, seeds, step=0, epoch=0):
         seeds = np.asarray(seeds, np.int32)
         B = len(seeds)
         cap = self.capacity or capacity_for(max(B, 1), self.fanout.tolist())
@@ -126,7 +127,7 @@ class Sampler:
         nc = np.zeros(16, np.int32)
         ec = np.zeros(16, np.int32)
         a = SampleArgs(self.n, _p(self.indptr), _p(self.indices), len(self.fanout), _p(self.fanout),
-                       self.rng_mode, self.rng_seed, step, cap, B,
+                       self.rng_mode, self.rng_seed, step, epoch, cap, B,
                        _p(out["sampled_ids"]), _p(out["agg_src_ids"]), _p(out["agg_dst_ids"]),
                        _p(out["agg_src_off"]), _p(out["agg_dst_off"]), _p(nc), _p(ec), _p(self.pos),
                        _p(self.topo_hotness), _p(self.node_hotness), self.n_threads)
@@ -137,11 +138,11 @@ class Sampler:
         return out
 
 
-def draw_hop(indptr, indices, frontier, f, rng_mode=RNG_MINSTD, rng_seed=0, hop=0, step=0):
+def draw_hop(indptr, indices, frontier, f, rng_mode=RNG_MINSTD, rng_seed=0, hop=0, step=0, epoch=0):
     frontier = np.ascontiguousarray(frontier, np.int32)
     out = np.empty(len(frontier) * f, np.int32)
     lib().lgo_draw_hop(_p(indptr), _p(indices), _p(frontier), C.c_int64(len(frontier)), C.c_int32(f), C.c_int32(rng_mode),
-                       C.c_uint64(rng_seed), C.c_uint32(hop), C.c_uint32(step), _p(out))
+                       C.c_uint64(rng_seed), C.c_uint32(hop), C.c_uint32(step), C.c_uint32(epoch), _p(out))
     return out
 
 

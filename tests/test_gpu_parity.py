@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 INT_KEYS = ("nc", "ec", "sampled_ids", "agg_src_ids", "agg_dst_ids", "agg_src_off", "agg_dst_off")
 
 
-def _oracle_batch(O, smp, seeds, step):
-    out = smp.sample(seeds, step=step)
+def _oracle_batch(O, smp, seeds, step, epoch=0):
+    out = smp.sample(seeds, step=step, epoch=epoch)
     total, n_e = int(out["nc"][0]), int(out["ec"][0])
     res = {k: out[k] for k in ("nc", "ec")}
     res["sampled_ids"] = out["sampled_ids"][:total]
@@ -60,6 +60,31 @@ def test_sampling_bit_exact(c1, rng, fanout, dedup, monkeypatch):
         want = _oracle_batch(O, smp, seeds, step)
         _assert_same(got, want, ctx=f"{rng} {fanout} step {step}: ")
         assert r.status() == 0
+    r.close()
+
+
+def test_philox_epoch_and_step_offset_key_the_stream(c1):
+    """Philox counter = (slot, epoch, hop, step): the same seeds redrawn in another epoch / at another step offset give
+    other neighbourhoods, each bit-exact against the oracle keyed the same way (the reference's
+    minstd stream redraws identical neighbourhoods every epoch, Kernels.cu:402-405)."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    B, fanout = 512, [10, 5]
+    r = _make_runner(L, c1, B, fanout, L.RNG_PHILOX, feat=False)
+    smp = O.Sampler(c1.indptr, c1.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=7)
+    seeds = c1.train_ids[:B]
+    seen = []
+    for epoch, off, step in ((0, 0, 3), (1, 0, 3), (2, 0, 3), (1, 100, 3), (1, 0, 103)):
+        r.set_epoch(epoch, off)
+        r.batch_from_host(seeds, None, step=step)
+        for h in range(len(fanout)):
+            r.sample_hop(h)
+        r.finish_batch()
+        got = r.fetch(with_features=False)
+        _assert_same(got, _oracle_batch(O, smp, seeds, step + off, epoch=epoch), ctx=f"epoch {epoch} off {off}: ")
+        seen.append(got["agg_src_ids"].copy())
+    assert not np.array_equal(seen[0], seen[1]) and not np.array_equal(seen[1], seen[2])
+    assert np.array_equal(seen[3], seen[4])              # offset + step is what enters the counter
     r.close()
 
 

@@ -43,16 +43,16 @@ def test_philox_matches_libcudacxx_fixture_and_random123_kat():
 
 
 # ---- independent pure-Python restatement of the reference kernels (small cases only) ----
-def _py_pick(mode, idx, hop, step, seed, deg, f, k):
+def _py_pick(mode, idx, hop, step, seed, deg, f, k, epoch=0):
     if mode == O.RNG_MINSTD:
         x = pow(48271, idx + 1, 2147483647)                       # minstd_rand().discard(idx) then one draw
         return int((x - 1) / 2147483646.0 * deg)                  # uniform_int_distribution via double
     if deg <= f:
         return k
-    return (O.philox4x32_10([idx & 0xffffffff, idx >> 32, hop, step], [seed & 0xffffffff, seed >> 32])[0] * deg) >> 32
+    return (O.philox4x32_10([idx & 0xffffffff, epoch, hop, step], [seed & 0xffffffff, seed >> 32])[0] * deg) >> 32   # counter = (slot, epoch, hop, step)
 
 
-def _py_reference_batch(indptr, indices, seeds, fanout, mode, seed, step):
+def _py_reference_batch(indptr, indices, seeds, fanout, mode, seed, step, epoch=0):
     """Kernels.cu:68-96 (batch_generator), 342-448 (sampler), 450-463 (construct_graph),
     112-150 (update_counter) executed slot by slot in idx order."""
     ids = [int(s) for s in seeds]
@@ -74,7 +74,7 @@ def _py_reference_batch(indptr, indices, seeds, fanout, mode, seed, step):
             start, deg = int(indptr[s]), int(indptr[s + 1] - indptr[s])
             if k >= deg:
                 continue
-            d = int(indices[start + _py_pick(mode, idx, h, step, seed, deg, f, k)])
+            d = int(indices[start + _py_pick(mode, idx, h, step, seed, deg, f, k, epoch)])
             if d < 0:
                 continue
             if d not in pos:
@@ -144,6 +144,24 @@ def test_threaded_oracle_is_identical(c1):
         b = O.Sampler(d.indptr, d.indices, [25, 10], rng_mode=mode, rng_seed=5, n_threads=4)
         x, y = a.sample(d.train_ids[:1024], step=3), b.sample(d.train_ids[:1024], step=3)
         assert all(np.array_equal(x[k], y[k]) for k in x)
+
+
+def test_philox_epoch_word(small):
+    """counter word 1 = epoch: another epoch redraws other neighbourhoods of the same seeds; epoch 0 is the
+    round-1 stream (slot index in word 0, zero in word 1)."""
+    d = small
+    smp = O.Sampler(d.indptr, d.indices, [3, 2], rng_mode=O.RNG_PHILOX, rng_seed=5)
+    seeds = d.train_ids[:40]
+    outs = []
+    for epoch in (0, 1, 7):
+        got = smp.sample(seeds, step=2, epoch=epoch)
+        want = _py_reference_batch(d.indptr, d.indices, seeds, [3, 2], O.RNG_PHILOX, 5, 2, epoch=epoch)
+        n_e = int(want["ec"][0])
+        assert np.array_equal(got["ec"], want["ec"]) and np.array_equal(got["agg_src_ids"][:n_e], want["agg_src_ids"])
+        outs.append(got["agg_src_ids"][:n_e].copy())
+    assert not np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[1], outs[2])
+    assert O.philox_pick(123, 1, 9, 5, 1000, epoch=0) == (O.philox4x32_10([123, 0, 1, 9], [5, 0])[0] * 1000) >> 32
+    assert O.philox_pick(123, 1, 9, 5, 1000, epoch=4) == (O.philox4x32_10([123, 4, 1, 9], [5, 0])[0] * 1000) >> 32
 
 
 def test_philox_full_neighbourhood_and_step_dependence(small):

@@ -201,6 +201,10 @@ static int ipc_main(int argc, char** argv)
     int seq = 0;
     CK(cudaSetDevice(rank));
     float *table, *out;
+    if (getenv("PROBE_PREALLOC_MB")) {   // stands in for the dataset a product process holds before it allocates its shard
+        void* dummy; CK(cudaMalloc(&dummy, (size_t)atoll(getenv("PROBE_PREALLOC_MB")) << 20));
+    }
+    const int n_kinds = getenv("PROBE_KINDS") ? atoi(getenv("PROBE_KINDS")) : 6;
     CK(cudaMalloc(&table, max_table));
     CK(cudaMalloc(&out, (size_t)n_rows * row_f * 4));
     cudaStream_t s; CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -232,7 +236,7 @@ static int ipc_main(int argc, char** argv)
     for (size_t sz : sizes) {
         if (sz > max_table) continue;
         const long long rows_per_tab = (long long)(sz / ((size_t)row_f * 4));
-        for (int kind = 0; kind < 6; kind++) {
+        for (int kind = 0; kind < n_kinds; kind++) {
             file_barrier(dir, rank, world, seq);
             for (int rep = -1; rep < reps; rep++) {
                 if (rep == 0) CK(cudaEventRecord(e0, s));
