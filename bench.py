@@ -579,11 +579,34 @@ def run_b200(args):
 
     # ---- parity: one mini-batch of THIS rank against the CPU oracle, through the real tier mappings ----
     oracle_state = {}
+    shm_files = []
+
+    def host_csr():
+        """the CSR in host memory for the oracle; with several ranks ONE copy in /dev/shm is shared by all of them
+        (8 private copies of papers100M's 7.4 GB CSR would not fit every box)."""
+        if world == 1:
+            return ds.indptr.cpu().numpy(), ds.indices.cpu().numpy()
+        tok = [os.urandom(4).hex() if rank == 0 else None]
+        dist.broadcast_object_list(tok, src=0)
+        paths = ["/dev/shm/lgn_bench_%s_%s" % (tok[0], nm) for nm in ("indptr", "indices")]
+        specs = [(ds.indptr, np.int64), (ds.indices, np.int32)]
+        if rank == 0:
+            for path, (t, dt) in zip(paths, specs):
+                m = np.memmap(path, dtype=dt, mode="w+", shape=(t.numel(),))
+                step_ = 1 << 26
+                for lo in range(0, t.numel(), step_):
+                    m[lo:lo + step_] = t[lo:lo + step_].cpu().numpy()
+                m.flush()
+                del m
+                shm_files.append(path)
+        dist.barrier()
+        return tuple(np.memmap(path, dtype=dt, mode="r", shape=(t.numel(),)) for path, (t, dt) in zip(paths, specs))
 
     def parity_check(c, step=0, epoch=1):
         from oracle import oracle as O
         if "smp" not in oracle_state:
-            oracle_state["smp"] = O.Sampler(ds.indptr.cpu().numpy(), ds.indices.cpu().numpy(), fanout,
+            ip_h, ix_h = host_csr()
+            oracle_state["smp"] = O.Sampler(ip_h, ix_h, fanout,
                                             rng_mode=O.RNG_PHILOX if args.rng == "philox" else O.RNG_MINSTD, rng_seed=42,
                                             n_threads=max(1, (os.cpu_count() or 8) // max(1, world)))
         seeds = my_train[step * B:(step + 1) * B].cpu().numpy()
@@ -903,6 +926,13 @@ def run_b200(args):
     line["extra"]["bench_wall_s"] = time.perf_counter() - t_start
     if rank == 0:
         emit(line)
+    if world > 1:
+        dist.barrier()
+    for path in shm_files:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
     if world > 1:
         drop_cache(c)
         dist.barrier()

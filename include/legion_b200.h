@@ -174,6 +174,8 @@ int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_
 int lgn_select_pipe(lgn_ctx* ctx, int32_t pipe);
 int lgn_wait_pipe(lgn_ctx* ctx, void* stream, int32_t pipe);
 int lgn_sync_pipe(lgn_ctx* ctx, int32_t pipe);
+/* lgn_sync_pipe + the slot's sticky device status (0 or LGN_E_CAPACITY) in one call */
+int lgn_sync_pipe_status(lgn_ctx* ctx, int32_t pipe);
 
 /* ------------------------------------------------------------------ results */
 typedef struct {
@@ -250,7 +252,31 @@ int lgn_fill_topo_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_
 int lgn_cost_model(const uint32_t* af_sorted_dev, const uint32_t* at_sorted_dev, const int32_t* qt_dev,
                    const int64_t* indptr_dev, int64_t n, int32_t dim, int64_t cache_memory, int32_t kg,
                    uint64_t topo_trans, const int32_t* max_ids, int32_t train_step,
-                   int32_t* node_capacity, int32_t* edge_capacity);
+                   int32_t* node_capacity, int32_t* edge_capacity, void* stream);
+/* B200 placement model (no reference counterpart): how many of the hottest feature rows to replicate on
+ * every GPU of the clique before the rest is partitioned and what stays on the host, given the per-GPU byte budget for
+ * features and the three tier bandwidths (any common unit).  af_sorted_dev = presampled hotness in hot order (the
+ * sorted counts of lgn_hot_order).  Outputs feed lgn_place_hybrid / lgn_fill_feature_shard_hybrid: *n_repl rows are
+ * replicated, *cap is the shard height. */
+int lgn_plan_hybrid(const uint32_t* af_sorted_dev, int64_t n, int32_t dim, int64_t budget_bytes, int32_t kg,
+                    double bw_local, double bw_peer, double bw_host, int64_t* n_repl, int64_t* cap, double* est_cost,
+                    void* stream);
+
+/* ------------------------------------------------------------------ collective
+ * The path's one collective: the sum of the per-GPU hotness histograms before planning.  Replaces the leader's P2P
+ * reads of aggregate_access (GPUCache.cu:44-48, 624-647) with an NCCL all-reduce of u32[N]; NCCL is
+ * resolved with dlopen at first use (LGN_E_SYS when it is absent). */
+int lgn_comm_available(void);
+/* one process drives the GPUs of the clique (the `legion` server): bufs[i] is device memory of devices[i]; blocks
+ * until every buffer holds the element-wise sum */
+int lgn_allreduce_u32_devices(int32_t n_devices, const int32_t* devices, uint32_t* const* bufs, int64_t count);
+/* one process per GPU: rank 0 makes the 128-byte NCCL unique id, the caller ships it to the other ranks, every rank
+ * creates its communicator with its GPU current, then all-reduces in place on a stream */
+typedef struct lgn_comm lgn_comm;
+int lgn_comm_unique_id(uint8_t id[128]);
+int lgn_comm_create(int32_t rank, int32_t world, const uint8_t id[128], lgn_comm** out);
+int lgn_comm_allreduce_u32(lgn_comm* comm, uint32_t* buf_dev, int64_t count, void* stream);
+int lgn_comm_destroy(lgn_comm* comm);
 
 /* ------------------------------------------------------------------ IPC wire format
  * server side of CUDA_IPC_Service (CUDA_IPC_Service.cu:34-359): POSIX shm

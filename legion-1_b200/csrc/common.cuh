@@ -7,13 +7,22 @@
 
 namespace lgn {
 
-// ---- slot_map encoding -------------------------------------------------
-// One int32 per node replaces the reference's dedup bitmap + position_map
-// (Kernels.cu:88-92, 412-438).  value < CAND  : final local index of the node
-//                               CAND + slot   : smallest slot that sampled it this hop
-//                               EMPTY         : not in the current batch
+// ---- dedup value encoding ------------------------------------------------
+// One 32-bit value per node of the batch replaces the reference's dedup bitmap + position_map
+// (Kernels.cu:88-92, 412-438):
+//     [31] 0   [30:25] generation   [24] CAND   [23:0] payload
+// payload without CAND : final local index of the node
+// payload with CAND    : smallest slot of the current hop that sampled the node (a candidate)
+// EMPTY                : generation 63, never written by a batch
+// Every value a batch writes carries the batch's generation, and generations DEcrease from batch to batch
+// (62, 61, .., 0, then the table is reset): a red.min therefore overwrites whatever an older batch left
+// behind, and nothing has to be released at the end of a batch (the reference memsets N/8 bytes per batch and
+// clears its position map entry by entry, Kernels.cu:750-756).
 constexpr int32_t EMPTY = 0x7fffffff;
-constexpr int32_t CAND = 0x40000000;
+constexpr int GEN_SHIFT = 25;
+constexpr int N_GEN = 63;
+constexpr int32_t CAND = 1 << 24;
+constexpr int32_t PAYLOAD_MASK = (1 << GEN_SHIFT) - 1;
 
 // ---- per-batch device state (written by kernels, never read by the host on
 // the hot path) ----------------------------------------------------------
@@ -30,6 +39,9 @@ struct BatchState {
     int32_t status;         // sticky: 0 or LGN_E_CAPACITY
     int32_t max_ids;        // max unique ids over presampled batches (GPUCache.cu:294-296)
     uint32_t epoch;         // philox counter word 1
+    int32_t gen_base;       // generation of this batch << GEN_SHIFT (dedup values, see above)
+    uint32_t done_ctr;      // CTAs of k_mark that have finished (the last one scans the tile counts)
+    int32_t pad2[2];
     unsigned long long tier_rows[4];   // local, peer, host rows gathered
     unsigned long long tot_items;      // frontier items expanded since the last reset (every hop)
     unsigned long long tot_edges;      // edges sampled since the last reset
@@ -101,13 +113,12 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint4 v, unsigned long lon
 }
 
 // ---- per-batch dedup structure ------------------------------------------------------------
-// Two interchangeable layouts behind one interface (DESIGN.md section 5):
-//   direct  int32 map[N]: value < CAND final local index, CAND+slot candidate, EMPTY unused.  One probe per
-//           access, but N*4 bytes per lane: L2-resident only for small graphs.
+// Two interchangeable layouts behind one interface (DESIGN.md section 3):
+//   direct  int32 map[N]: one probe per access, but 4N bytes per lane: L2-resident only for small graphs.
 //   hash    open-addressing table of (key << 32 | value) words sized for the BATCH (2^bits entries, a few MB),
-//           so it stays in L2 whatever N is.  64-bit atomicMin keeps the smallest value of a key because the key
+//           so it stays in L2 whatever N is.  A 64-bit red.min keeps the smallest value of a key because the key
 //           occupies the high word.  A claim returns the entry's index ("handle"); later passes address the
-//           entry directly, without probing.
+//           entry directly, without probing.  Entries of older generations count as free.
 constexpr unsigned long long EMPTY64 = ~0ull;
 
 struct Dedup {
@@ -126,18 +137,13 @@ __device__ __forceinline__ void st_keep_u64(unsigned long long* p, unsigned long
 {
     asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ unsigned long long cas_keep_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val,
-                                                            unsigned long long)
-{
-    return atomicCAS(p, cmp, val);   // ptxas rejects .L2::cache_hint on atom.cas; the ld/red that follow carry the policy
-}
 __device__ __forceinline__ void red_min_keep_u64(unsigned long long* p, unsigned long long v, unsigned long long pol)
 {
     asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
 
-// lower the value stored for `key` to `val` (claim the node for slot `val - CAND`, or for seed index `val`);
-// returns the entry's handle, or -1 if the hash table is full (reported through BatchState::status)
+// lower the value stored for `key` to `val` (generation | payload); returns the entry's handle, or -1 if the hash
+// table is full (reported through BatchState::status)
 __device__ __forceinline__ int32_t dedup_claim(const Dedup& dd, int32_t key, int32_t val, unsigned long long keep)
 {
     if (dd.bits == 0) { red_min_keep(&dd.map[key], val, keep); return key; }
@@ -147,12 +153,15 @@ __device__ __forceinline__ int32_t dedup_claim(const Dedup& dd, int32_t key, int
     h ^= h >> 13; h *= 0xc2b2ae35u;
     h ^= h >> 16;
     h &= mask;
+    const uint32_t gen = (uint32_t)val >> GEN_SHIFT;
     const unsigned long long mine = ((unsigned long long)(uint32_t)key << 32) | (uint32_t)val;
     for (int probe = 0; probe < 1024; probe++) {
         unsigned long long cur = ld_keep_u64(dd.tab + h, keep);
-        if (cur == EMPTY64) {
-            cur = cas_keep_u64(dd.tab + h, EMPTY64, mine, keep);
-            if (cur == EMPTY64) return (int32_t)h;
+        if (((uint32_t)cur >> GEN_SHIFT) != gen) {                 // free: never used (EMPTY64 is generation 63) or left by an older batch
+            const unsigned long long seen = atomicCAS(dd.tab + h, cur, mine);   // ptxas rejects .L2::cache_hint on atom.cas
+            if (seen == cur) return (int32_t)h;
+            cur = seen;                                              // somebody of this batch took it: fall through and look at it
+            if (((uint32_t)cur >> GEN_SHIFT) != gen) { probe--; continue; }
         }
         if ((uint32_t)(cur >> 32) == (uint32_t)key) {
             if ((uint32_t)cur > (uint32_t)val) red_min_keep_u64(dd.tab + h, mine, keep);   // values only ever decrease
@@ -162,19 +171,24 @@ __device__ __forceinline__ int32_t dedup_claim(const Dedup& dd, int32_t key, int
     }
     return -1;
 }
-__device__ __forceinline__ int32_t dedup_value(const Dedup& dd, int32_t handle, unsigned long long keep)
+// payload (CAND | slot, or final index) of an entry claimed in this batch
+__device__ __forceinline__ int32_t dedup_payload(const Dedup& dd, int32_t handle, unsigned long long keep)
 {
-    return dd.bits == 0 ? ld_keep(&dd.map[handle], keep) : (int32_t)(uint32_t)ld_keep_u64(dd.tab + handle, keep);
+    const int32_t v = dd.bits == 0 ? ld_keep(&dd.map[handle], keep) : (int32_t)(uint32_t)ld_keep_u64(dd.tab + handle, keep);
+    return v & PAYLOAD_MASK;
 }
-__device__ __forceinline__ void dedup_publish(const Dedup& dd, int32_t handle, int32_t key, int32_t pos, unsigned long long keep)
+// payload and key in one access (the hash entry holds both; a direct-map handle IS the key)
+__device__ __forceinline__ int32_t dedup_payload_key(const Dedup& dd, int32_t handle, int32_t& key, unsigned long long keep)
 {
-    if (dd.bits == 0) st_keep(&dd.map[handle], pos, keep);
-    else st_keep_u64(dd.tab + handle, ((unsigned long long)(uint32_t)key << 32) | (uint32_t)pos, keep);
+    if (dd.bits == 0) { key = handle; return ld_keep(&dd.map[handle], keep) & PAYLOAD_MASK; }
+    const unsigned long long e = ld_keep_u64(dd.tab + handle, keep);
+    key = (int32_t)(uint32_t)(e >> 32);
+    return (int32_t)(uint32_t)e & PAYLOAD_MASK;
 }
-__device__ __forceinline__ void dedup_release(const Dedup& dd, int32_t handle, unsigned long long keep)
+__device__ __forceinline__ void dedup_publish(const Dedup& dd, int32_t handle, int32_t key, int32_t val, unsigned long long keep)
 {
-    if (dd.bits == 0) st_keep(&dd.map[handle], EMPTY, keep);
-    else st_keep_u64(dd.tab + handle, EMPTY64, keep);
+    if (dd.bits == 0) st_keep(&dd.map[handle], val, keep);
+    else st_keep_u64(dd.tab + handle, ((unsigned long long)(uint32_t)key << 32) | (uint32_t)val, keep);
 }
 
 // ---- thrust::minstd_rand compatibility (Kernels.cu:402-405) ----------------

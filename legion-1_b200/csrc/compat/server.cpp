@@ -314,6 +314,7 @@ public:
             }
             CUDA_DIE(cudaStreamSynchronize(streams_[1]));
             CUDA_DIE(cudaStreamSynchronize(streams_[0]));
+            LGN_DIE(lgn_sync_pipe_status(st_.ctx, pipe_), "mini-batch (device status)");
             LGN_DIE(lgn_ipc_server_post(env_->ipc, dev_, pipe_), "IPCPost");
         } else {
             LGN_DIE(lgn_batch_generate(st_.ctx, streams_[pipe_], pipe_, st_.mode, st_.batch_size, st_.iter), "lgn_batch_generate");
@@ -343,7 +344,8 @@ public:
 private:
     void Publish(int pipe)
     {
-        LGN_DIE(lgn_sync_pipe(st_.ctx, pipe), "lgn_sync_pipe");
+        // a truncated block must never reach a trainer: capacity overflow (dedup table, id / edge / feature buffers) is fatal
+        LGN_DIE(lgn_sync_pipe_status(st_.ctx, pipe), "mini-batch (device status)");
         LGN_DIE(lgn_ipc_server_post(env_->ipc, dev_, pipe), "IPCPost");
     }
     int dev_ = 0, op_num_ = 0, pipe_ = 0, inflight_ = -1;
@@ -424,9 +426,15 @@ public:
         for (auto& t : th) t.join();
         // hash dedup (large graphs): size the per-batch table for what presampling saw instead of the worst case,
         // so that it stays L2-resident (2.5x the largest batch inside the call; no-op for the direct map)
+        // Presampling only saw TRAIN batches of raw_batch seeds; a valid/test batch may carry more seeds, so the estimate
+        // is scaled by the largest batch any mode can have (overflow would be caught by Publish, but must not happen).
         for (int i = 0; i < n_; i++) {
-            const int32_t seen = lgn_max_ids(ctx_[i], nullptr);
-            if (seen > 0) LGN_DIE(lgn_set_dedup_capacity(ctx_[i], seen), "lgn_set_dedup_capacity");
+            const int64_t seen = lgn_max_ids(ctx_[i], nullptr);
+            int64_t largest = ds_.batch;
+            if (env_.steps.valid_batch[i] > largest) largest = env_.steps.valid_batch[i];
+            if (env_.steps.test_batch[i] > largest) largest = env_.steps.test_batch[i];
+            const int64_t expect = (seen * largest + ds_.batch - 1) / ds_.batch;
+            if (expect > 0) LGN_DIE(lgn_set_dedup_capacity(ctx_[i], expect), "lgn_set_dedup_capacity");
         }
         int kg = cache_agg_mode == 1 ? 2 : cache_agg_mode == 2 ? 4 : cache_agg_mode == 3 ? 8 : 1;   // GPUCache.cu:593-607
         if (kg > n_) {   // the reference computes Kc = 0 here and serves without any cache
@@ -443,8 +451,20 @@ public:
             LGN_DIE(lgn_hotness(ctx_[lead], &nh, &th2), "lgn_hotness");
             std::vector<int32_t> max_ids(kg);
             uint64_t trans = 0;
-            for (int j = 0; j < kg; j++) {                                             // CandidateSelection: sum the clique
-                if (j > 0) {
+            // CandidateSelection: sum the clique's histograms.  NCCL all-reduce over NVLink (every GPU ends up with the
+            // sum); the reference's leader-reads-peers loop (aggregate_access) remains as the fallback without NCCL.
+            bool summed = false;
+            if (kg > 1 && lgn_comm_available() && !getenv("LEGION_NO_NCCL")) {
+                std::vector<int32_t> devs(kg);
+                std::vector<uint32_t*> nptr(kg), tptr2(kg);
+                for (int j = 0; j < kg; j++) { devs[j] = lead + j; LGN_DIE(lgn_hotness(ctx_[lead + j], &nptr[j], &tptr2[j]), "lgn_hotness"); }
+                LGN_DIE(lgn_allreduce_u32_devices(kg, devs.data(), nptr.data(), N), "ncclAllReduce(node hotness)");
+                LGN_DIE(lgn_allreduce_u32_devices(kg, devs.data(), tptr2.data(), N), "ncclAllReduce(topology hotness)");
+                std::cout << "Hotness all-reduce: NCCL over " << kg << " GPUs\n";
+                summed = true;
+            }
+            for (int j = 0; j < kg; j++) {
+                if (j > 0 && !summed) {
                     uint32_t *pn = nullptr, *pt = nullptr;
                     LGN_DIE(lgn_hotness(ctx_[lead + j], &pn, &pt), "lgn_hotness");
                     LGN_DIE(lgn_set_device(lead), "set device");
@@ -464,8 +484,39 @@ public:
             LGN_DIE(lgn_hot_order(nh, N, (int32_t*)qf, (uint32_t*)af, nullptr), "hot order (features)");
             LGN_DIE(lgn_hot_order(th2, N, (int32_t*)qt, (uint32_t*)at, nullptr), "hot order (topology)");
             int32_t ncap = 0, ecap = 0;
+            int64_t n_repl = 0;
             const int64_t feat_bytes = N * ds_.dim * 4, topo_bytes = 8 * N + 4 * ds_.n_edges;
-            if (ds_.cache_memory * kg > feat_bytes + topo_bytes + (int64_t)kg * (8 + ds_.dim * 4)) {
+            const char* pl = getenv("LEGION_PLACEMENT");
+            const bool hybrid = !(pl && !strcmp(pl, "reference"));
+            bool topo_replicated = false;
+            if (hybrid) {
+                // B200 placement.  Topology: a full copy in every GPU's HBM when it takes at most a quarter of the
+                // budget (7.4 GB for papers100M), otherwise the reference's partition with the capacity its cost model picks.
+                // Features: lgn_plan_hybrid splits the remaining budget into rows replicated on every GPU of the clique, rows
+                // partitioned over it and rows left on the host, by expected gather time over the three tiers.
+                int64_t feat_budget = ds_.cache_memory;
+                if (topo_bytes + 8 <= ds_.cache_memory / 4) {
+                    topo_replicated = true;
+                    feat_budget -= topo_bytes + 8;
+                } else {
+                    int32_t ncap_ref = 0;
+                    LGN_DIE(lgn_cost_model((uint32_t*)af, (uint32_t*)at, (int32_t*)qt, ds_.indptr_d, N, ds_.dim, ds_.cache_memory, kg, trans,
+                                           max_ids.data(), train_step, &ncap_ref, &ecap, nullptr), "CostModel(topology)");
+                    const int64_t avg_adj = 8 + 4 * (ds_.n_edges / (N > 0 ? N : 1) + 1);
+                    const int64_t topo_share = (int64_t)ecap * avg_adj;
+                    if (topo_share > ds_.cache_memory / 2) ecap = (int32_t)(ds_.cache_memory / 2 / avg_adj);
+                    feat_budget -= (int64_t)ecap * avg_adj;
+                }
+                if (feat_budget < ds_.dim * 4) feat_budget = ds_.dim * 4;
+                int64_t cap64 = 0;
+                double cost = 0;
+                const double bw_local = 3272.0, bw_peer = 640.0, bw_host = 50.0;     // GB/s payload per GPU: HBM copy / 2, measured NVLink gather, PCIe Gen5 zero-copy
+                LGN_DIE(lgn_plan_hybrid((uint32_t*)af, N, ds_.dim, feat_budget, kg, bw_local, bw_peer, bw_host, &n_repl, &cap64, &cost, nullptr), "lgn_plan_hybrid");
+                ncap = (int32_t)cap64;
+                if (topo_replicated) ecap = 0;
+                std::cout << "Placement: hybrid, " << n_repl << " hottest rows replicated, " << (cap64 - n_repl) * kg << " partitioned over " << kg
+                          << " GPU(s), topology " << (topo_replicated ? "replicated in HBM" : "partitioned") << "\n";
+            } else if (ds_.cache_memory * kg > feat_bytes + topo_bytes + (int64_t)kg * (8 + ds_.dim * 4)) {
                 // Everything fits.  The reference's CostModel leaves both capacity tables at 0 in this case
                 // (GPUCache.cu:744-751 only fill them while a tier does NOT fit) and would cache one row; with
                 // 180 GB per B200 this is the normal case, so it is handled explicitly: cache all of both tiers.
@@ -473,7 +524,7 @@ public:
                 std::cout << "Cost model: whole graph fits, caching everything\n";
             } else {
                 LGN_DIE(lgn_cost_model((uint32_t*)af, (uint32_t*)at, (int32_t*)qt, ds_.indptr_d, N, ds_.dim, ds_.cache_memory, kg, trans,
-                                       max_ids.data(), train_step, &ncap, &ecap), "CostModel");
+                                       max_ids.data(), train_step, &ncap, &ecap, nullptr), "CostModel");
             }
             std::cout << "Feat capacity " << ncap << " topo capacity " << ecap << std::endl;
             // FillUp (GPUCache.cu:769-826): shard j of the clique lives on GPU lead+j
@@ -492,14 +543,21 @@ public:
                 void *shard = nullptr, *fs = nullptr, *ts = nullptr, *tip = nullptr, *tix = nullptr;
                 LGN_DIE(lgn_device_alloc(&shard, (int64_t)ncap * ds_.dim * 4), "alloc feature shard");
                 LGN_DIE(lgn_device_alloc(&fs, N * 4), "alloc"); LGN_DIE(lgn_device_alloc(&ts, N * 4), "alloc");
-                LGN_DIE(lgn_fill_feature_shard((int32_t*)oq, N, ncap, kg, j, ds_.feat_d, ds_.dim, (float*)shard, nullptr), "FeatFillUp");
-                LGN_DIE(lgn_place((int32_t*)oq, N, ncap, kg, (int32_t*)fs, nullptr), "InitPair");
-                LGN_DIE(lgn_place((int32_t*)ot, N, ecap, kg, (int32_t*)ts, nullptr), "InitIndexPair");
-                LGN_DIE(lgn_device_alloc(&tip, (int64_t)(ecap + 1) * 8), "alloc");
-                int64_t cnt = 0;
-                LGN_DIE(lgn_fill_topo_shard((int32_t*)ot, N, ecap, kg, j, ds_.indptr_d, ds_.indices_d, (int64_t*)tip, nullptr, &cnt, nullptr), "GetNeighborCount");
-                LGN_DIE(lgn_device_alloc(&tix, (cnt > 0 ? cnt : 1) * 4), "alloc");
-                LGN_DIE(lgn_fill_topo_shard((int32_t*)ot, N, ecap, kg, j, ds_.indptr_d, ds_.indices_d, (int64_t*)tip, (int32_t*)tix, &cnt, nullptr), "TopoFillUp");
+                LGN_DIE(lgn_fill_feature_shard_hybrid((int32_t*)oq, N, ncap, kg, j, n_repl, ds_.feat_d, ds_.dim, (float*)shard, nullptr), "FeatFillUp");
+                LGN_DIE(lgn_place_hybrid((int32_t*)oq, N, ncap, kg, n_repl, j, (int32_t*)fs, nullptr), "InitPair");
+                if (topo_replicated) {      // full CSR copy in this GPU's HBM: the sampler never leaves the device
+                    LGN_DIE(lgn_device_alloc(&tip, (int64_t)(N + 1) * 8), "alloc");
+                    LGN_DIE(lgn_device_alloc(&tix, (ds_.n_edges > 0 ? ds_.n_edges : 1) * 4), "alloc");
+                    LGN_DIE(lgn_copy_h2d(tip, ds_.indptr_h, (int64_t)(N + 1) * 8), "copy indptr");
+                    LGN_DIE(lgn_copy_h2d(tix, ds_.indices_h, ds_.n_edges * 4), "copy indices");
+                } else {
+                    LGN_DIE(lgn_place((int32_t*)ot, N, ecap, kg, (int32_t*)ts, nullptr), "InitIndexPair");
+                    LGN_DIE(lgn_device_alloc(&tip, (int64_t)(ecap + 1) * 8), "alloc");
+                    int64_t cnt = 0;
+                    LGN_DIE(lgn_fill_topo_shard((int32_t*)ot, N, ecap, kg, j, ds_.indptr_d, ds_.indices_d, (int64_t*)tip, nullptr, &cnt, nullptr), "GetNeighborCount");
+                    LGN_DIE(lgn_device_alloc(&tix, (cnt > 0 ? cnt : 1) * 4), "alloc");
+                    LGN_DIE(lgn_fill_topo_shard((int32_t*)ot, N, ecap, kg, j, ds_.indptr_d, ds_.indices_d, (int64_t*)tip, (int32_t*)tix, &cnt, nullptr), "TopoFillUp");
+                }
                 LGN_DIE(lgn_device_synchronize(), "sync");
                 fshard[j] = (float*)shard; fslot[j] = (int32_t*)fs; tslot[j] = (int32_t*)ts; tptr[j] = (int64_t*)tip; tidx[j] = (int32_t*)tix;
                 for (void* q : {shard, fs, ts, tip, tix}) owned_.push_back({dev, q});
@@ -508,7 +566,8 @@ public:
             for (int j = 0; j < kg; j++) {   // every GPU of the clique sees all shards (P2P) and its own replica of the maps
                 LGN_DIE(lgn_set_part(ctx_[lead + j], j), "lgn_set_part");
                 LGN_DIE(lgn_bind_feature_cache(ctx_[lead + j], kg, fshard.data(), fslot[j], ncap), "bind feature cache");
-                LGN_DIE(lgn_bind_topology_cache(ctx_[lead + j], kg, tptr.data(), tidx.data(), tslot[j], ecap), "bind topology cache");
+                if (topo_replicated) LGN_DIE(lgn_bind_topology(ctx_[lead + j], tptr[j], tidx[j]), "bind topology (HBM copy)");
+                else LGN_DIE(lgn_bind_topology_cache(ctx_[lead + j], kg, tptr.data(), tidx.data(), tslot[j], ecap), "bind topology cache");
             }
             LGN_DIE(lgn_set_device(lead), "set device");
             lgn_device_free(qf); lgn_device_free(qt); lgn_device_free(af); lgn_device_free(at);

@@ -171,7 +171,7 @@ int lgn_create(const lgn_config* cfg, lgn_ctx** out)
         cur *= cfg->fanout[h];
         cap += cur;
         if (cur > max_slots) max_slots = cur;
-        if (cap >= lgn::CAND) return LGN_E_ARG;         // slot indices must stay below the CAND tag
+        if (cap >= lgn::CAND || cur >= lgn::CAND) return LGN_E_ARG;   // local indices and slot indices must fit the 24-bit payload of a dedup value
     }
     CK(cudaSetDevice(cfg->device));
     lgn_ctx* c = new (std::nothrow) lgn_ctx();
@@ -207,13 +207,11 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         while (((long long)1 << bits) < 2 * cap && bits < 30) bits++;
         c->dedup_bits_max = bits;
     }
-    long long slots_total = 0;
-    {
-        long long cur2 = cfg->batch_size;
-        for (int h = 0; h < cfg->n_hops; h++) { c->slot_off[h] = slots_total; cur2 *= cfg->fanout[h]; slots_total += (cur2 + 15) / 16 * 16; }
-        for (int h = cfg->n_hops; h <= LGN_MAX_HOPS; h++) c->slot_off[h] = slots_total;
+    {   // tiles of the widest hop (k_sample: sample_items_per_tile() frontier items each)
+        long long items = cfg->batch_size, widest = cfg->batch_size;
+        for (int h = 1; h < cfg->n_hops; h++) { items *= cfg->fanout[h - 1]; if (items > widest) widest = items; }
+        c->max_tiles = (widest + lgn::sample_items_per_tile() - 1) / lgn::sample_items_per_tile() + 1;
     }
-    const long long n_tiles = (max_slots + 1023) / 1024 + 1;   // >= tiles of any RESOLVE_TILE >= 1024
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int p = 0; p < c->n_lanes; p++) {      // CUDA_IPC_Service.cu:140-215, Server.cu:217-231
@@ -231,8 +229,8 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
             const size_t entries = (size_t)1 << c->dedup_bits_max;
             CK(malloc_pages(&pp.dedup_tab, entries * sizeof(unsigned long long)));
             CK(cudaMemset(pp.dedup_tab, 0xFF, entries * sizeof(unsigned long long)));
-            CK(malloc_pages(&pp.slot_h, (max_slots + 16) * sizeof(int32_t)));
-            CK(malloc_pages(&pp.id_h, cap * sizeof(int32_t)));
+            CK(malloc_pages(&pp.seed_h, (size_t)cfg->batch_size * sizeof(int32_t)));
+            CK(malloc_pages(&pp.draw_key, (max_slots + 16) * sizeof(int32_t)));
             pp.dedup.map = nullptr; pp.dedup.tab = pp.dedup_tab; pp.dedup.bits = c->dedup_bits_max;
         } else {
             CK(malloc_pages(&pp.slot_map, (size_t)cfg->n_nodes * sizeof(int32_t)));
@@ -240,9 +238,13 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         }
         CK(malloc_pages(&pp.agg_src_ids, cap * sizeof(int32_t)));
         CK(malloc_pages(&pp.agg_dst_ids, cap * sizeof(int32_t)));
-        CK(malloc_pages(&pp.slot_dst, (slots_total + 16) * sizeof(int32_t)));
-        CK(malloc_pages(&pp.slot_val, (max_slots + 16) * sizeof(int32_t)));
-        CK(malloc_pages(&pp.tile_cnt, n_tiles * sizeof(unsigned long long)));
+        CK(malloc_pages(&pp.draw_h, (max_slots + 16) * sizeof(int32_t)));
+        CK(malloc_pages(&pp.draw_s, (max_slots + 16) * sizeof(uint16_t)));
+        CK(malloc_pages(&pp.draw_v, (max_slots + 16) * sizeof(int32_t)));
+        CK(malloc_pages(&pp.tile_n, c->max_tiles * sizeof(int32_t)));
+        CK(malloc_pages(&pp.tile_new, c->max_tiles * sizeof(int32_t)));
+        CK(malloc_pages(&pp.pre_e, c->max_tiles * sizeof(int32_t)));
+        CK(malloc_pages(&pp.pre_n, c->max_tiles * sizeof(int32_t)));
         CK(malloc_pages(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
         CK(malloc_pages(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
@@ -275,7 +277,7 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         if (c->gather_threads > 256) c->gather_threads = 256;
         c->gather_threads = (c->gather_threads + 31) / 32 * 32;
         c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
-        c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 4);
+        c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 12);   // 128-thread CTAs, one tile per iteration
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
         const char* ug = getenv("LGN_GRAPH");
         c->use_graphs = ug ? atoi(ug) : 1;
@@ -305,8 +307,9 @@ int lgn_destroy(lgn_ctx* c)
         lgn::Pipe& pp = c->pipe[p];
         cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
         cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
-        cudaFree(pp.slot_map); cudaFree(pp.dedup_tab); cudaFree(pp.slot_h); cudaFree(pp.id_h); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids); cudaFree(pp.slot_dst); cudaFree(pp.slot_val);
-        cudaFree(pp.tile_cnt); cudaFree(pp.state); cudaFree(pp.seed_stage);
+        cudaFree(pp.slot_map); cudaFree(pp.dedup_tab); cudaFree(pp.seed_h); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids);
+        cudaFree(pp.draw_h); cudaFree(pp.draw_s); cudaFree(pp.draw_v); cudaFree(pp.draw_key); cudaFree(pp.tile_n); cudaFree(pp.tile_new);
+        cudaFree(pp.pre_e); cudaFree(pp.pre_n); cudaFree(pp.state); cudaFree(pp.seed_stage);
         if (pp.gather_stream) cudaStreamDestroy(pp.gather_stream);
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
         if (pp.ev_end) cudaEventDestroy(pp.ev_end);
@@ -327,10 +330,13 @@ int lgn_set_dedup_capacity(lgn_ctx* c, int64_t expected_unique)
 {
     if (!c || expected_unique <= 0) return LGN_E_ARG;
     if (!c->dedup_hash) return LGN_OK;
-    for (int i = 0; i < c->n_lanes; i++) if (c->pipe[i].pending) CK(cudaEventSynchronize(c->pipe[i].ev_done));   // tables are empty between batches
+    for (int i = 0; i < c->n_lanes; i++) if (c->pipe[i].pending) CK(cudaEventSynchronize(c->pipe[i].ev_done));
     uint32_t bits = 10;
     while (((long long)1 << bits) < (5 * expected_unique) / 2 && bits < c->dedup_bits_max) bits++;
-    for (int i = 0; i < c->n_lanes; i++) c->pipe[i].dedup.bits = bits;
+    for (int i = 0; i < c->n_lanes; i++) {      // entries move when the table shrinks or grows: start from an empty one
+        c->pipe[i].dedup.bits = bits;
+        CK(cudaMemset(c->pipe[i].dedup_tab, 0xFF, sizeof(unsigned long long) << bits));
+    }
     invalidate_graphs(c);
     return LGN_OK;
 }
@@ -454,7 +460,15 @@ int lgn_profile_enable(lgn_ctx* c, int32_t max_records)
     c->prof_ev = new cudaEvent_t[2 * (size_t)max_records];
     c->prof_kind = new signed char[max_records];
     c->prof_pipe = new signed char[max_records];
-    for (int i = 0; i < 2 * max_records; i++) CK(cudaEventCreate(&c->prof_ev[i]));
+    for (int i = 0; i < 2 * max_records; i++) {
+        cudaError_t e = cudaEventCreate(&c->prof_ev[i]);
+        if (e != cudaSuccess) {          // release what exists: a failed enable leaves profiling off, nothing leaked
+            for (int k = 0; k < i; k++) cudaEventDestroy(c->prof_ev[k]);
+            delete[] c->prof_ev; delete[] c->prof_kind; delete[] c->prof_pipe;
+            c->prof_ev = nullptr; c->prof_kind = nullptr; c->prof_pipe = nullptr;
+            return lgn_cuda_fail(e, "cudaEventCreate");
+        }
+    }
     c->prof_cap = max_records;
     return LGN_OK;
 }
@@ -517,7 +531,7 @@ int lgn_debug_shard_read(lgn_ctx* c, void* stream, int32_t slot, int64_t n_rows,
 // ---------------------------------------------------------------- hot path
 int lgn_batch_generate(lgn_ctx* c, void* stream, int32_t pipe, int32_t mode, int32_t batch_size, int32_t counter)
 {
-    if (!c || pipe < 0 || pipe >= c->n_lanes || mode < 0 || mode > 2 || batch_size <= 0 || counter < 0) return LGN_E_ARG;
+    if (!c || pipe < 0 || pipe >= c->n_lanes || mode < 0 || mode > 2 || batch_size < 0 || counter < 0) return LGN_E_ARG;   // 0 = empty batch (a partition without valid/test ids)
     if (batch_size > c->cfg.batch_size) return LGN_E_CAPACITY;
     if (!c->seed_ids[mode]) return LGN_E_STATE;
     const int32_t total = c->seed_count[mode];
@@ -769,6 +783,17 @@ int lgn_tier_counts(lgn_ctx* c, void* stream, int64_t out[3], int32_t reset)
     return LGN_OK;
 }
 
+// host-blocking: waits for the slot's batch and returns ITS sticky status (0 or LGN_E_CAPACITY): what a server checks
+// before it hands the slot to a trainer
+int lgn_sync_pipe_status(lgn_ctx* c, int32_t pipe)
+{
+    if (!c || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
+    if (c->pipe[pipe].pending) CK(cudaEventSynchronize(c->pipe[pipe].ev_done));
+    int32_t st = 0;
+    CK(cudaMemcpy(&st, &c->pipe[pipe].state->status, 4, cudaMemcpyDeviceToHost));
+    return st;
+}
+
 int lgn_status(lgn_ctx* c, void* stream)
 {
     if (!c) return LGN_E_ARG;
@@ -875,3 +900,13 @@ int32_t lgn_local_batch_id(const lgn_steps* s, int32_t epochs, int32_t g)
 }
 
 }  // extern "C"
+
+// start of a generation cycle: every value of the lane's dedup structure back to EMPTY (every 63rd batch of a slot)
+namespace lgn {
+void reset_dedup(lgn_ctx* c, Pipe& p, cudaStream_t s)
+{
+    if (c->dedup_hash) cudaMemsetAsync(p.dedup_tab, 0xFF, sizeof(unsigned long long) << p.dedup.bits, s);
+    else k_fill_i32<<<1024, 256, 0, s>>>(p.slot_map, lgn::EMPTY, c->cfg.n_nodes);
+}
+}  // namespace lgn
+

@@ -43,13 +43,19 @@ struct Pipe {
     Dedup dedup;               // direct int32[N] map or batch-sized hash table (common.cuh)
     unsigned long long* dedup_tab;   // hash allocation (2^dedup_bits_max entries)
     int32_t* slot_map;         // direct allocation, int32[N]
-    int32_t* slot_h;           // int32[max slots of a hop]: hash handles of the draws
-    int32_t* id_h;             // int32[capacity]: hash handle of every id of the batch
+    int32_t* seed_h;           // hash layout: int32[B], dedup handle of every seed (-1: table full)
     int32_t* agg_src_ids;      // raw ids, int32[capacity]
     int32_t* agg_dst_ids;
-    int32_t* slot_dst;         // int32[sum of slots over hops]: draw results, then winners' local indices
-    int32_t* slot_val;         // int32[max slots of a hop]: slot_map value probed by k_mark
-    unsigned long long* tile_cnt;      // packed (valid, new) count per 2048-slot tile of the current hop
+    // per-hop scratch, tile t of a hop owns [t * 32 * f, (t + 1) * 32 * f): the hop's valid draws, compacted per tile
+    int32_t* draw_h;           // int32[max slots of a hop]: dedup handle of the draw (direct layout: the node id)
+    uint16_t* draw_s;          // slot of the draw inside its tile
+    int32_t* draw_v;           // payload probed by k_mark
+    int32_t* draw_key;         // hash layout: the node id read with the payload
+    int32_t* tile_n;           // int32[max tiles of a hop]: valid draws (= edges) of the tile
+    int32_t* tile_new;         // new unique nodes of the tile
+    int32_t* pre_e;            // exclusive prefixes of the two counts
+    int32_t* pre_n;
+    unsigned long long batch_seq;   // batches started in this slot: generation = 62 - seq % 63
     BatchState* state;         // device
     int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
     cudaStream_t gather_stream;
@@ -73,7 +79,7 @@ struct lgn_ctx {
     lgn::Pipe pipe[LGN_MAX_LANES];
     int n_lanes;
     int cur_pipe;
-    long long slot_off[LGN_MAX_HOPS + 1];   // start of hop h's region inside slot_dst
+    long long max_tiles;       // tiles of the widest hop
     uint32_t* node_hotness;    // u32[N] or NULL
     uint32_t* topo_hotness;
     // bound storage
@@ -108,6 +114,9 @@ void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const in
                         int32_t count, uint32_t step);
 void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc);
 void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
+int sample_items_per_tile();
+// context.cu
+void reset_dedup(lgn_ctx* c, Pipe& p, cudaStream_t s);
 // gather.cu
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs);
 void gather_init_device();

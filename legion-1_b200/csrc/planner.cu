@@ -91,26 +91,30 @@ __global__ void k_widen(const uint32_t* __restrict__ in, unsigned long long* __r
 
 using namespace lgn;
 
+// temporary device buffer released on every exit path
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
 extern "C" int lgn_hot_order(const uint32_t* counts, int64_t n, int32_t* order, uint32_t* sorted_counts, void* stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (!counts || !order || n <= 0 || n > 0x7fffffffLL) return LGN_E_ARG;
-    int32_t* iota = nullptr;
-    uint32_t* keys_out = sorted_counts;
-    void* tmp = nullptr;
+    DevBuf iota, keys, tmp;
     size_t tmp_bytes = 0;
-    CK(cudaMalloc(&iota, n * sizeof(int32_t)));
-    if (!keys_out) CK(cudaMalloc(&keys_out, n * sizeof(uint32_t)));
-    k_iota<<<1024, 256, 0, s>>>(iota, n);
+    CK(iota.alloc(n * sizeof(int32_t)));
+    uint32_t* keys_out = sorted_counts;
+    if (!keys_out) { CK(keys.alloc(n * sizeof(uint32_t))); keys_out = keys.as<uint32_t>(); }
+    k_iota<<<1024, 256, 0, s>>>(iota.as<int32_t>(), n);
     // stable LSD radix sort, descending keys, payload = iota  ==> (count desc, id asc):
     // the order thrust::sort_by_key(greater) yields in the reference (GPUCache.cu:630-631)
-    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, counts, keys_out, iota, order, (int)n, 0, 32, s));
-    CK(cudaMalloc(&tmp, tmp_bytes));
-    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, counts, keys_out, iota, order, (int)n, 0, 32, s));
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, counts, keys_out, iota.as<int32_t>(), order, (int)n, 0, 32, s));
+    CK(tmp.alloc(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairsDescending(tmp.p, tmp_bytes, counts, keys_out, iota.as<int32_t>(), order, (int)n, 0, 32, s));
     CK(cudaStreamSynchronize(s));
-    cudaFree(tmp);
-    cudaFree(iota);
-    if (!sorted_counts) cudaFree(keys_out);
     return LGN_OK;
 }
 
@@ -155,20 +159,17 @@ extern "C" int lgn_fill_topo_shard(const int32_t* order, int64_t n, int64_t cap,
     cudaStream_t s = (cudaStream_t)stream;
     if (!order || !indptr || !indptr_out || kg <= 0 || j < 0 || j >= kg || cap <= 0) return LGN_E_ARG;
     if (!indices_out) {
-        int64_t* deg = nullptr;
-        void* tmp = nullptr;
+        DevBuf deg, tmp;
         size_t tmp_bytes = 0;
-        CK(cudaMalloc(&deg, cap * sizeof(int64_t)));
-        k_shard_degrees<<<1024, 256, 0, s>>>(order, n, cap, kg, j, indptr, deg);
+        CK(deg.alloc(cap * sizeof(int64_t)));
+        k_shard_degrees<<<1024, 256, 0, s>>>(order, n, cap, kg, j, indptr, deg.as<int64_t>());
         CK(cudaMemsetAsync(indptr_out, 0, sizeof(int64_t), s));
-        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, deg, indptr_out + 1, (int)cap, s));
-        CK(cudaMalloc(&tmp, tmp_bytes));
-        CK(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, deg, indptr_out + 1, (int)cap, s));
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, deg.as<int64_t>(), indptr_out + 1, (int)cap, s));
+        CK(tmp.alloc(tmp_bytes));
+        CK(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, deg.as<int64_t>(), indptr_out + 1, (int)cap, s));
         int64_t total = 0;
         CK(cudaMemcpyAsync(&total, indptr_out + cap, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        cudaFree(tmp);
-        cudaFree(deg);
         if (n_indices) *n_indices = total;
         return LGN_OK;
     }
@@ -178,62 +179,163 @@ extern "C" int lgn_fill_topo_shard(const int32_t* order, int64_t n, int64_t cap,
     return LGN_OK;
 }
 
-// CostModel (GPUCache.cu:661-767): prefix sums on the device, the 100-step sweep on the
-// host with the reference's arithmetic (float tables, double ratios).
+namespace lgn {
+// one sweep point of the cost model: how many nodes' adjacency lists / feature rows fit in `mem` bytes and how much
+// presampled hotness they cover.  The three prefix arrays stay on the device (the reference copies all of them to the
+// host, 3 x 8N bytes); one thread per sweep point does the binary search.
+struct SweepPoint { long long nt; unsigned long long edge_hot, node_hot; };
+__global__ void k_sweep(const unsigned long long* __restrict__ node_prefix, const unsigned long long* __restrict__ edge_prefix,
+                        const unsigned long long* __restrict__ mem_prefix, long long n, long long memory_step, long long steps,
+                        const long long* __restrict__ nf_of_step, SweepPoint* __restrict__ out)
+{
+    const long long cs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cs >= steps) return;
+    const unsigned long long cur = (unsigned long long)(cs * memory_step);
+    long long nt;
+    if (cur > mem_prefix[n - 1]) nt = n;
+    else {                                     // first index whose cumulative adjacency bytes reach `cur`
+        long long lo = 0, hi = n;
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (mem_prefix[mid] < cur) lo = mid + 1; else hi = mid; }
+        nt = lo;
+    }
+    const long long nf = nf_of_step[cs];
+    SweepPoint sp;
+    sp.nt = nt;
+    sp.edge_hot = (nt > 0 && nt <= n) ? edge_prefix[nt - 1] : 0;
+    sp.node_hot = (nf > 0 && nf <= n) ? node_prefix[nf - 1] : 0;
+    out[cs] = sp;
+}
+}  // namespace lgn
+
+// CostModel (GPUCache.cu:661-767).  Capacities must equal the reference's bit for bit (tests/test_reference_ab.py), so
+// the table arithmetic keeps its float / double conversions; the data movement does not follow it: prefix sums and the
+// per-step lookups run on the device, 101 sweep points come back instead of three N-element arrays.
 extern "C" int lgn_cost_model(const uint32_t* af, const uint32_t* at, const int32_t* qt, const int64_t* indptr, int64_t n,
                               int32_t dim, int64_t cache_memory, int32_t kg, uint64_t topo_trans, const int32_t* max_ids,
-                              int32_t train_step, int32_t* node_capacity, int32_t* edge_capacity)
+                              int32_t train_step, int32_t* node_capacity, int32_t* edge_capacity, void* stream)
 {
-    if (!af || !at || !qt || !indptr || n <= 0 || kg <= 0 || !max_ids || !node_capacity || !edge_capacity) return LGN_E_ARG;
-    unsigned long long *w = nullptr, *node_prefix = nullptr, *edge_prefix = nullptr, *mem_prefix = nullptr;
-    void* tmp = nullptr;
-    size_t tmp_bytes = 0;
-    CK(cudaMalloc(&w, n * 8)); CK(cudaMalloc(&node_prefix, n * 8)); CK(cudaMalloc(&edge_prefix, n * 8)); CK(cudaMalloc(&mem_prefix, n * 8));
-    CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, w, node_prefix, (int)n));
-    CK(cudaMalloc(&tmp, tmp_bytes));
-    k_widen<<<1024, 256>>>(af, w, n);
-    CK(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, w, node_prefix, (int)n));
-    k_widen<<<1024, 256>>>(at, w, n);
-    CK(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, w, edge_prefix, (int)n));
-    k_edge_mem<<<1024, 256>>>(qt, n, indptr, w);
-    CK(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, w, mem_prefix, (int)n));
-    std::vector<unsigned long long> h_node(n), h_edge(n), h_mem(n);
-    CK(cudaMemcpy(h_node.data(), node_prefix, n * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(h_edge.data(), edge_prefix, n * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(h_mem.data(), mem_prefix, n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(w); cudaFree(node_prefix); cudaFree(edge_prefix); cudaFree(mem_prefix); cudaFree(tmp);
-
-    const int max_payload = 64;                                                   // CLS, GPUCache.cu:31
-    int64_t memory_step = (int64_t)((double)(cache_memory * kg) * 0.01);          // :674
-    if (memory_step < 1) memory_step = 1;
-    uint64_t feat_trans = 0;
-    for (int i = 0; i < kg; i++)                                                  // :677-679
-        feat_trans += (uint64_t)(((((int64_t)max_ids[i] * train_step) * dim) * (int64_t)sizeof(float)) / max_payload);
+    if (!af || !at || !qt || !indptr || n <= 0 || kg <= 0 || dim <= 0 || cache_memory <= 0 || !max_ids || !node_capacity || !edge_capacity)
+        return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
     const int64_t total_mem = cache_memory * kg;
+    int64_t memory_step = (int64_t)((double)total_mem * 0.01);                    // 1 % of the clique's budget (:674)
+    if (memory_step < 1) memory_step = 1;
     const int64_t steps = (total_mem - 1) / memory_step + 1;
-    std::vector<float> t_topo(steps + 1, 0.f), t_feat(steps + 1, 0.f), c_topo(steps + 1, 0.f), c_feat(steps + 1, 0.f), t_total(steps + 1, 0.f);
-    int64_t cs = 0;
-    for (int64_t cur = 0; cur < total_mem; cur += memory_step) {                  // :723-753
-        int32_t nf, nt;
-        if ((uint64_t)cur > (uint64_t)n * dim * sizeof(float)) nf = (int32_t)n;
-        else nf = (int32_t)((uint64_t)(cs + 1) * ((uint64_t)memory_step / (dim * sizeof(float))));
-        if ((uint64_t)cur > h_mem[n - 1]) nt = (int32_t)n;
-        else nt = (int32_t)(std::lower_bound(h_mem.begin(), h_mem.end(), (unsigned long long)cur) - h_mem.begin());
-        if (nt < n) {
-            const unsigned long long ep = nt > 0 ? h_edge[nt - 1] : 0;            // reference reads [-1] at step 0 (unused)
-            t_topo[cs] = (float)((double)topo_trans * 1.0 / (double)h_edge[n - 1] * (double)ep);
-            c_topo[cs] = (float)(nt / kg);
+    const uint64_t row = (uint64_t)dim * sizeof(float);
+    std::vector<long long> nf_of_step(steps);
+    for (int64_t cs = 0; cs < steps; cs++) {                                      // feature rows that fit at sweep point cs (:728-731)
+        const uint64_t cur = (uint64_t)(cs * memory_step);
+        nf_of_step[cs] = cur > (uint64_t)n * row ? (long long)n : (long long)(int32_t)((uint64_t)(cs + 1) * ((uint64_t)memory_step / row));
+    }
+    DevBuf w, node_prefix, edge_prefix, mem_prefix, tmp, d_nf, d_out;
+    size_t tmp_bytes = 0;
+    CK(w.alloc(n * 8)); CK(node_prefix.alloc(n * 8)); CK(edge_prefix.alloc(n * 8)); CK(mem_prefix.alloc(n * 8));
+    CK(d_nf.alloc(steps * sizeof(long long))); CK(d_out.alloc(steps * sizeof(SweepPoint)));
+    auto* W = w.as<unsigned long long>();
+    CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, W, node_prefix.as<unsigned long long>(), (int)n, s));
+    CK(tmp.alloc(tmp_bytes));
+    k_widen<<<1024, 256, 0, s>>>(af, W, n);
+    CK(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, W, node_prefix.as<unsigned long long>(), (int)n, s));
+    k_widen<<<1024, 256, 0, s>>>(at, W, n);
+    CK(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, W, edge_prefix.as<unsigned long long>(), (int)n, s));
+    k_edge_mem<<<1024, 256, 0, s>>>(qt, n, indptr, W);
+    CK(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, W, mem_prefix.as<unsigned long long>(), (int)n, s));
+    CK(cudaMemcpyAsync(d_nf.p, nf_of_step.data(), steps * sizeof(long long), cudaMemcpyHostToDevice, s));
+    k_sweep<<<(unsigned)((steps + 127) / 128), 128, 0, s>>>(node_prefix.as<unsigned long long>(), edge_prefix.as<unsigned long long>(),
+                                                           mem_prefix.as<unsigned long long>(), n, memory_step, steps, d_nf.as<long long>(),
+                                                           d_out.as<SweepPoint>());
+    std::vector<SweepPoint> pts(steps);
+    unsigned long long node_total = 0, edge_total = 0;
+    CK(cudaMemcpyAsync(pts.data(), d_out.p, steps * sizeof(SweepPoint), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&node_total, node_prefix.as<unsigned long long>() + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&edge_total, edge_prefix.as<unsigned long long>() + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+
+    uint64_t feat_trans = 0;                                                      // 64-byte transactions of one epoch's gathers (:677-679)
+    for (int i = 0; i < kg; i++) feat_trans += (uint64_t)(((((int64_t)max_ids[i] * train_step) * dim) * (int64_t)sizeof(float)) / 64);
+    // saved transactions per sweep point: topology gets the first cs per cent of the budget, features the rest (:723-760)
+    std::vector<float> saved_topo(steps + 1, 0.f), saved_feat(steps + 1, 0.f), cap_topo(steps + 1, 0.f), cap_feat(steps + 1, 0.f);
+    for (int64_t cs = 0; cs < steps; cs++) {
+        const long long nt = pts[cs].nt, nf = nf_of_step[cs];
+        if (nt < n) {      // a tier that fits completely keeps gain 0 (the reference's quirk, :744-751)
+            saved_topo[cs] = (float)((double)topo_trans * 1.0 / (double)edge_total * (double)pts[cs].edge_hot);
+            cap_topo[cs] = (float)(nt / kg);
         }
         if (nf < n) {
-            const unsigned long long np = nf > 0 ? h_node[nf - 1] : 0;
-            t_feat[cs] = (float)((double)feat_trans * 1.0 / (double)h_node[n - 1] * (double)np);
-            c_feat[cs] = (float)(nf / kg);
+            saved_feat[cs] = (float)((double)feat_trans * 1.0 / (double)node_total * (double)pts[cs].node_hot);
+            cap_feat[cs] = (float)(nf / kg);
         }
-        cs++;
     }
-    for (int64_t sidx = 1; sidx < steps; sidx++) t_total[sidx] = t_topo[sidx] + t_feat[steps - 1 - sidx];   // :755-760
-    const int64_t best = std::max_element(t_total.begin(), t_total.end()) - t_total.begin();
-    *node_capacity = (int32_t)(c_feat[steps - 1 - best] + 1);                     // :763-764
-    *edge_capacity = (int32_t)(c_topo[best] + 1);
+    int64_t best = 0;
+    float best_saved = 0.f;                                                       // max_element: first maximum, entry 0 is 0 (:755-762)
+    for (int64_t cs = 1; cs < steps; cs++) {
+        const float tot = saved_topo[cs] + saved_feat[steps - 1 - cs];
+        if (tot > best_saved) { best_saved = tot; best = cs; }
+    }
+    *node_capacity = (int32_t)(cap_feat[steps - 1 - best] + 1);
+    *edge_capacity = (int32_t)(cap_topo[best] + 1);
+    return LGN_OK;
+}
+
+// B200 placement model (no reference counterpart).  The reference decides "topology vs features" against
+// PCIe transactions; on a B200 clique the decision that matters is how many of the hottest rows to REPLICATE on every
+// GPU (served from local HBM) before the rest is partitioned over the clique (1/kg local, the rest over NVLink) and
+// what stays on the host.  For n_repl replicated rows the per-GPU budget leaves room for (budget/row - n_repl) * kg
+// partitioned rows; the expected time of one epoch's gathers is
+//     t = H(n_repl)/bw_local + [H(n_repl + n_part) - H(n_repl)] * (1/kg/bw_local + (kg-1)/kg/bw_peer) + [H(N) - H(n_repl + n_part)]/bw_host
+// with H the cumulative presampled hotness in hot order.  101 candidate splits are evaluated, the cheapest wins.
+extern "C" int lgn_plan_hybrid(const uint32_t* af_sorted, int64_t n, int32_t dim, int64_t budget_bytes, int32_t kg,
+                               double bw_local, double bw_peer, double bw_host, int64_t* n_repl_out, int64_t* cap_out,
+                               double* est_cost, void* stream)
+{
+    if (!af_sorted || n <= 0 || dim <= 0 || budget_bytes <= 0 || kg <= 0 || kg > LGN_MAX_PARTS || !n_repl_out || !cap_out) return LGN_E_ARG;
+    if (!(bw_local > 0) || !(bw_peer > 0) || !(bw_host > 0)) return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t row = (int64_t)dim * 4;
+    const int64_t budget_rows = budget_bytes / row;
+    const int n_pts = 101;
+    DevBuf w, prefix, tmp;
+    size_t tmp_bytes = 0;
+    CK(w.alloc(n * 8)); CK(prefix.alloc(n * 8));
+    auto* W = w.as<unsigned long long>();
+    auto* H = prefix.as<unsigned long long>();
+    CK(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, W, H, (int)n, s));
+    CK(tmp.alloc(tmp_bytes));
+    k_widen<<<1024, 256, 0, s>>>(af_sorted, W, n);
+    CK(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, W, H, (int)n, s));
+    auto h_at = [&](int64_t k, unsigned long long* out) -> int {   // H(k) = hotness of the k hottest rows
+        *out = 0;
+        if (k <= 0) return LGN_OK;
+        if (k > n) k = n;
+        CK(cudaMemcpyAsync(out, H + (k - 1), 8, cudaMemcpyDeviceToHost, s));
+        return LGN_OK;
+    };
+    std::vector<int64_t> repl(n_pts), part(n_pts);
+    std::vector<unsigned long long> h_repl(n_pts), h_all(n_pts);
+    unsigned long long total = 0;
+    const int64_t max_repl = budget_rows < n ? budget_rows : n;
+    for (int i = 0; i < n_pts; i++) {
+        repl[i] = kg == 1 ? 0 : max_repl * i / (n_pts - 1);
+        int64_t room = (budget_rows - repl[i]) * kg;
+        if (room > n - repl[i]) room = n - repl[i];
+        part[i] = room < 0 ? 0 : room;
+        int rc;
+        if ((rc = h_at(repl[i], &h_repl[i]))) return rc;
+        if ((rc = h_at(repl[i] + part[i], &h_all[i]))) return rc;
+    }
+    { int rc; if ((rc = h_at(n, &total))) return rc; }
+    CK(cudaStreamSynchronize(s));
+    const double c_mix = 1.0 / kg / bw_local + (double)(kg - 1) / kg / bw_peer;
+    int best = 0;
+    double best_t = -1.0;
+    for (int i = 0; i < n_pts; i++) {
+        const double t = (double)h_repl[i] / bw_local + (double)(h_all[i] - h_repl[i]) * c_mix + (double)(total - h_all[i]) / bw_host;
+        if (best_t < 0 || t < best_t) { best_t = t; best = i; }
+        if (kg == 1) break;
+    }
+    *n_repl_out = repl[best];
+    *cap_out = repl[best] + (part[best] + kg - 1) / kg;
+    if (*cap_out < 1) *cap_out = 1;
+    if (est_cost) *est_cost = best_t * (double)row;      // expected seconds per presampled epoch if the bandwidths are bytes/s
     return LGN_OK;
 }

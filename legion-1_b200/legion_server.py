@@ -33,7 +33,7 @@ def main(argv=None):
     ap.add_argument("--epoch", type=int, default=10)
     ap.add_argument("--cache_memory", type=int, default=38000000000)
     ap.add_argument("--usenvlink", type=int, default=1)
-    ap.add_argument("--cache_agg_mode", type=int, default=-1, help="-1: the reference's rule; 0/1/2/3 = 1/2/4/8 GPUs per clique")
+    ap.add_argument("--cache_agg_mode", type=int, default=-1, help="-1: one clique over all GPUs (NVSwitch); 0/1/2/3 = 1/2/4/8 GPUs per clique")
     ap.add_argument("--rng", type=str, default="minstd", choices=["minstd", "philox"])
     ap.add_argument("--custom", type=str, default="", help="path,vertices,edges,dim,train,valid,test for a dataset outside the table")
     ap.add_argument("--dry_run", action="store_true")
@@ -55,7 +55,10 @@ def main(argv=None):
                                                           1 - a.usenvlink))
     mode = a.cache_agg_mode
     if mode < 0:
-        mode = 1 if (a.usenvlink == 1 and a.gpu_number >= 2) else 0          # legion_server.py:62-68
+        # The reference pairs GPUs (Kg <= 2, legion_server.py:62-68) because its testbeds had NVLink bridges between pairs.
+        # On an NVSwitch node every GPU reaches every peer at full bandwidth, so the clique is the whole machine: Kg = P
+        # (mode 0/1/2/3 = 1/2/4/8 GPUs per clique, GPUCache.cu:593-607); a GPU count that is not a power of two keeps pairs.
+        mode = {1: 0, 2: 1, 4: 2, 8: 3}.get(a.gpu_number, 1 if a.gpu_number >= 2 else 0) if a.usenvlink == 1 else 0
     env = dict(os.environ, LEGION_FANOUT=a.nbrs_num.strip("[] ").replace(" ", ""), LEGION_RNG=a.rng)
     cmd = [LEGION, str(a.gpu_number), str(mode)]
     if a.dry_run:

@@ -307,8 +307,18 @@ def cost_model(af_sorted, at_sorted, qt, indptr, dim, cache_memory, kg, topo_tra
     ncap, ecap = C.c_int32(), C.c_int32()
     check(lib().lgn_cost_model(_ptr(af_sorted), _ptr(at_sorted), _ptr(qt), _ptr(indptr), C.c_int64(n), C.c_int32(dim),
                                C.c_int64(cache_memory), C.c_int32(kg), C.c_uint64(topo_trans), mi, C.c_int32(train_step),
-                               C.byref(ncap), C.byref(ecap)), "lgn_cost_model")
+                               C.byref(ncap), C.byref(ecap), None), "lgn_cost_model")
     return ncap.value, ecap.value
+
+
+def plan_hybrid(af_sorted, dim, budget_bytes, kg, bw_local, bw_peer, bw_host, stream=None):
+    """B200 placement model (lgn_plan_hybrid): -> (n_repl, cap, estimated cost)."""
+    n = af_sorted.shape[0]
+    n_repl, cap, cost = C.c_int64(), C.c_int64(), C.c_double()
+    check(lib().lgn_plan_hybrid(_ptr(af_sorted), C.c_int64(n), C.c_int32(dim), C.c_int64(int(budget_bytes)), C.c_int32(kg),
+                                C.c_double(bw_local), C.c_double(bw_peer), C.c_double(bw_host), C.byref(n_repl), C.byref(cap),
+                                C.byref(cost), _vp(stream)), "lgn_plan_hybrid")
+    return n_repl.value, cap.value, cost.value
 
 
 def coordinate(n_train, n_valid, n_test, batch, epochs):

@@ -31,7 +31,13 @@ def consume_and_check(dev, parts, n_nodes, avg_deg, dim, n_class, B, epochs, fan
     for g in range(st.max_step):
         mode, local = O.mode_of_step(st, epochs, g), O.local_batch_id(st, epochs, g)
         seeds, slab = O.batch_generate(lists[mode][0], lists[mode][1].astype(np.int32), mode_batch[mode], local)
-        want = smp.sample(seeds, step=local)
+        # Philox position used by the server (server.cpp RunOnce): epoch of the global batch id (+1: epoch 0 is the
+        # presampling pass), step = batch id inside the epoch + a per-mode offset
+        per_epoch = st.train_step + st.valid_step
+        is_test = g >= per_epoch * epochs
+        epoch = (epochs if is_test else (g // per_epoch if per_epoch else 0)) + 1
+        off = 0 if mode == 0 else (st.train_step if mode == 1 else per_epoch)
+        want = smp.sample(seeds, step=local + off, epoch=epoch)
         nc, ec = want["nc"], want["ec"]
         if len(fanout) != 2:        # additive k-hop consumer API (the reference's get_next is hard-wired to two hops)
             H = len(fanout)

@@ -268,6 +268,51 @@ def test_hybrid_placement_gather(kg, frac_repl, frac_shard):
         r.close()
 
 
+@pytest.mark.parametrize("kg,budget_frac", [(1, 0.3), (2, 0.4), (8, 0.2), (8, 0.6), (4, 2.0)])
+def test_plan_hybrid_picks_the_cheapest_split(kg, budget_frac):
+    """B200 placement model: of the 101 candidate splits (replicated / partitioned / host) the one with the smallest
+    expected gather time under the three tier bandwidths is chosen; restated here with numpy on the same candidates."""
+    import legion_b200 as L
+    n, dim = 50_000, 64
+    rng = np.random.default_rng(5)
+    counts = np.sort((rng.pareto(1.2, n) * 20).astype(np.uint32))[::-1].copy()       # hot order, heavy tail
+    row = dim * 4
+    budget = int(n * row * budget_frac)
+    bw_l, bw_p, bw_h = 3272.0, 640.0, 50.0
+    n_repl, cap, cost = L.plan_hybrid(L.DevArray.from_numpy(counts), dim, budget, kg, bw_l, bw_p, bw_h)
+    H = np.concatenate([[0], np.cumsum(counts.astype(np.uint64))]).astype(np.float64)
+    budget_rows = budget // row
+    best = None
+    for i in range(101):
+        rp = 0 if kg == 1 else min(budget_rows, n) * i // 100
+        part = max(0, min(n - rp, (budget_rows - rp) * kg))
+        t = H[rp] / bw_l + (H[rp + part] - H[rp]) * (1 / kg / bw_l + (kg - 1) / kg / bw_p) + (H[n] - H[rp + part]) / bw_h
+        if best is None or t < best[0]:
+            best = (t, rp, rp + (part + kg - 1) // kg)
+        if kg == 1:
+            break
+    assert (n_repl, cap) == (best[1], max(1, best[2]))
+    assert abs(cost - best[0] * row) <= 1e-9 * abs(cost)
+    if budget_frac >= 1.0:
+        assert H[n_repl] == H[n]                # everything fits on every GPU: all the presampled hotness is served locally
+    assert cap * row <= budget + row
+
+
+def test_empty_batch_is_accepted(small):
+    """a partition without valid/test ids yields batch size 0 (lgn_coordinate); the reference runs an empty batch."""
+    import legion_b200 as L
+    d = small
+    r = L.Runner(d.n_nodes, 0, 16, [3, 2])
+    r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+    ids = d.valid_ids[:5].astype(np.int32)
+    r.bind_seeds(L.MODE_VALID, L.DevArray.from_numpy(ids), L.DevArray.from_numpy(d.labels[ids]))
+    r.batch_generate(L.MODE_VALID, 0, 0)
+    r.run_batch(with_features=False)
+    got = r.fetch(with_features=False)
+    assert int(got["nc"][0]) == 0 and int(got["ec"][0]) == 0 and r.status() == 0
+    r.close()
+
+
 def test_debug_shard_read_copies_shard_rows():
     """lgn_debug_shard_read (diagnostic entry point): every output row must be a bit-exact copy of SOME row of the
     bound shards, peers_only must leave this GPU's own shard out, and argument checks must hold."""

@@ -306,7 +306,7 @@ def test_launcher_writes_reference_meta_config(tmp_path, monkeypatch, capsys):
     assert legion_server.main(["--dataset", "PR", "--dataset_path", "/data", "--gpu_number", "4", "--epoch", "3", "--dry_run"]) == 0
     f = open(tmp_path / "meta_config").read().split()
     assert f == ["/data/products/", "8000", "2449029", "123718280", "100", "196615", "39323", "2213091", "38000000000", "3", "0"]
-    assert capsys.readouterr().out.split()[-2:] == ["4", "1"]          # >= 2 GPUs with NVLink -> 2 GPUs per clique (reference rule)
+    assert capsys.readouterr().out.split()[-2:] == ["4", "2"]          # NVSwitch: one clique over all 4 GPUs (the reference pairs them: mode 1)
     assert legion_server.main(["--dataset", "PA", "--gpu_number", "8", "--cache_agg_mode", "3", "--usenvlink", "0", "--dry_run"]) == 0
     f = open(tmp_path / "meta_config").read().split()
     assert f[2:5] == ["111059956", "1615685872", "128"] and f[-1] == "1"
