@@ -443,7 +443,8 @@ def run_b200(args):
     # ---- presampling epoch (epoch 0) -> hotness -> all-reduce -> hot order -----------------
     r.set_epoch(0)
     t_pre = time.perf_counter()
-    for step in range(train_steps):
+    presample_steps = min(train_steps, int(os.environ.get("LGN_BENCH_PRESAMPLE_STEPS", train_steps)))   # profiling runs shorten the epoch
+    for step in range(presample_steps):
         r.batch_generate(L.MODE_TRAIN, B, step, stream=lp[step % NL], pipe=step % NL)
         r.run_batch(with_features=False, is_presc=True, stream=lp[step % NL])
     torch.cuda.synchronize()
@@ -460,8 +461,10 @@ def run_b200(args):
             grp = dist.new_group(backend="gloo") if dist.get_backend() == "nccl" else None
             dist.all_reduce(h, group=grp)
             nh_t.copy_(h)
-        else:
+        elif how == "torch":    # the same reduction through torch.distributed's communicator
             cluster.allreduce_hotness(dist, nh, n=N, device=dev)
+        else:                   # default: ncclAllReduce inside liblegion_b200.so (lgn_comm_*), torch only ships the unique id
+            cluster.native_allreduce_u32(dist, nh.ptr, N, stream=sp)
         torch.cuda.synchronize()
     order = L.hot_order(nh)
     kg = world

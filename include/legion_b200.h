@@ -192,6 +192,10 @@ typedef struct {
     int64_t max_rows;
 } lgn_batch_view;
 int lgn_batch_buffers(lgn_ctx* ctx, int32_t pipe, lgn_batch_view* out);
+/* the reverse: the caller owns the wire buffers of a slot (GPUMemoryPool::Set*, GPUMemoryPool.cuh:92-160; the reference
+ * runner allocates them itself or takes them from IPCEnv, Server.cu:217-283).  Non-NULL members of *v replace the
+ * slot's buffers; capacity / max_rows state their sizes; agg_src_ids / agg_dst_ids are ignored (lane-private). */
+int lgn_attach_buffers(lgn_ctx* ctx, int32_t pipe, const lgn_batch_view* v);
 /* D2H of both counter blocks on `stream` + stream sync: what ipc_service.get_next
  * does on the trainer side (ipc_cuda_kernel.cu:192-193). */
 int lgn_read_counters(lgn_ctx* ctx, void* stream, int32_t pipe, int32_t nc[16], int32_t ec[16]);

@@ -44,6 +44,27 @@ def allreduce_hotness(dist, hist, n=None, device=None):
     return t
 
 
+def native_allreduce_u32(dist, ptr, n, stream=None):
+    """in-place sum of a device u32[n] histogram over the ranks with the LIBRARY's own NCCL communicator
+    (lgn_comm_*: ncclAllReduce inside liblegion_b200.so); torch.distributed only ships the 128-byte unique id."""
+    import ctypes as C
+    from ._lib import lib, check
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(lib().lgn_comm_unique_id(uid), "lgn_comm_unique_id")
+    box = [bytes(uid) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    comm = C.c_void_p()
+    check(lib().lgn_comm_create(C.c_int32(rank), C.c_int32(world), uid, C.byref(comm)), "lgn_comm_create")
+    try:
+        check(lib().lgn_comm_allreduce_u32(comm, C.c_void_p(int(ptr)), C.c_int64(n), C.c_void_p(stream or 0)), "lgn_comm_allreduce_u32")
+        check(lib().lgn_stream_synchronize(C.c_void_p(stream or 0)), "lgn_stream_synchronize")
+    finally:
+        lib().lgn_comm_destroy(comm)
+
+
 def exchange_handles(dist, handle_bytes):
     """every rank contributes its 64-byte CUDA-IPC handle; returns the list indexed by rank."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1

@@ -40,7 +40,7 @@ struct BatchState {
     int32_t max_ids;        // max unique ids over presampled batches (GPUCache.cu:294-296)
     uint32_t epoch;         // philox counter word 1
     int32_t gen_base;       // generation of this batch << GEN_SHIFT (dedup values, see above)
-    uint32_t done_ctr;      // CTAs of k_mark that have finished (the last one scans the tile counts)
+    uint32_t pad1;
     int32_t pad2[2];
     unsigned long long tier_rows[4];   // local, peer, host rows gathered
     unsigned long long tot_items;      // frontier items expanded since the last reset (every hop)

@@ -243,8 +243,8 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         CK(malloc_pages(&pp.draw_v, (max_slots + 16) * sizeof(int32_t)));
         CK(malloc_pages(&pp.tile_n, c->max_tiles * sizeof(int32_t)));
         CK(malloc_pages(&pp.tile_new, c->max_tiles * sizeof(int32_t)));
-        CK(malloc_pages(&pp.pre_e, c->max_tiles * sizeof(int32_t)));
-        CK(malloc_pages(&pp.pre_n, c->max_tiles * sizeof(int32_t)));
+        CK(malloc_pages(&pp.super_e, (c->max_tiles / 64 + 2) * sizeof(int32_t)));
+        CK(malloc_pages(&pp.super_n, (c->max_tiles / 64 + 2) * sizeof(int32_t)));
         CK(malloc_pages(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
         CK(malloc_pages(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
@@ -276,7 +276,7 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         c->gather_threads = knob("LGN_GATHER_THREADS", 256);
         if (c->gather_threads > 256) c->gather_threads = 256;
         c->gather_threads = (c->gather_threads + 31) / 32 * 32;
-        c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 8);
+        c->sample_ctas_per_sm = knob("LGN_SAMPLE_CTAS", 16);
         c->resolve_ctas_per_sm = knob("LGN_RESOLVE_CTAS", 12);   // 128-thread CTAs, one tile per iteration
         c->end_ctas_per_sm = knob("LGN_END_CTAS", 4);
         const char* ug = getenv("LGN_GRAPH");
@@ -289,6 +289,10 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
             size_t want = (size_t)c->n_lanes * (c->dedup_hash ? ((size_t)8 << c->dedup_bits_max) : (size_t)cfg->n_nodes * 4);
             if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
             CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        }
+        if (const char* fg = getenv("LGN_L2_FETCH")) {      // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
+            cudaGetLastError();
         }
         const char* sg = getenv("LGN_SHARED_GATHER");
         c->shared_gather_stream = sg ? atoi(sg) : 0;
@@ -305,11 +309,11 @@ int lgn_destroy(lgn_ctx* c)
     cudaDeviceSynchronize();
     for (int p = 0; p < c->n_lanes; p++) {
         lgn::Pipe& pp = c->pipe[p];
-        cudaFree(pp.ids); cudaFree(pp.labels); cudaFree(pp.agg_src_off); cudaFree(pp.agg_dst_off);
-        cudaFree(pp.nc); cudaFree(pp.ec); cudaFree(pp.features);
+        void* wire[7] = {pp.ids, pp.features, pp.labels, pp.agg_src_off, pp.agg_dst_off, pp.nc, pp.ec};
+        for (int i = 0; i < 7; i++) if (!(pp.external & (1u << i))) cudaFree(wire[i]);     // attached buffers belong to the caller
         cudaFree(pp.slot_map); cudaFree(pp.dedup_tab); cudaFree(pp.seed_h); cudaFree(pp.agg_src_ids); cudaFree(pp.agg_dst_ids);
         cudaFree(pp.draw_h); cudaFree(pp.draw_s); cudaFree(pp.draw_v); cudaFree(pp.draw_key); cudaFree(pp.tile_n); cudaFree(pp.tile_new);
-        cudaFree(pp.pre_e); cudaFree(pp.pre_n); cudaFree(pp.state); cudaFree(pp.seed_stage);
+        cudaFree(pp.super_e); cudaFree(pp.super_n); cudaFree(pp.state); cudaFree(pp.seed_stage);
         if (pp.gather_stream) cudaStreamDestroy(pp.gather_stream);
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) if (pp.ev_hop[i]) cudaEventDestroy(pp.ev_hop[i]);
         if (pp.ev_end) cudaEventDestroy(pp.ev_end);
@@ -743,6 +747,38 @@ int lgn_batch_buffers(lgn_ctx* c, int32_t pipe, lgn_batch_view* v)
     v->ids = p.ids; v->features = p.features; v->labels = p.labels; v->agg_src = p.agg_src_off; v->agg_dst = p.agg_dst_off;
     v->node_counter = p.nc; v->edge_counter = p.ec; v->agg_src_ids = p.agg_src_ids; v->agg_dst_ids = p.agg_dst_ids;
     v->capacity = c->capacity; v->max_rows = c->max_rows;
+    return LGN_OK;
+}
+
+// A reference-style runner owns the seven wire buffers of a slot itself (Server.cu:217-283 allocates them, or takes
+// them from IPCEnv, and registers them in its GPUMemoryPool).  Every non-NULL pointer of *v replaces the slot's own
+// buffer (which is released); the caller keeps ownership and must keep them alive until lgn_destroy.  Sizes: ids and
+// the two edge arrays hold v->capacity entries, features v->max_rows rows; smaller buffers than the context's worst
+// case lower its limits (the reference sizes them from the raw batch and 1.2 x max_ids): overflow sets LGN_E_CAPACITY.
+int lgn_attach_buffers(lgn_ctx* c, int32_t pipe, const lgn_batch_view* v)
+{
+    if (!c || !v || pipe < 0 || pipe >= c->n_lanes) return LGN_E_ARG;
+    if ((v->ids || v->agg_src || v->agg_dst) && v->capacity < c->cfg.batch_size) return LGN_E_CAPACITY;   // not even the seeds fit
+    if (v->features && v->max_rows <= 0) return LGN_E_ARG;
+    if (((uintptr_t)v->agg_src | (uintptr_t)v->features) & 15) return LGN_E_ARG;      // 128-bit accesses (k_batch_end, the gathers)
+    lgn::Pipe& pp = c->pipe[pipe];
+    if (pp.pending) CK(cudaEventSynchronize(pp.ev_done));
+    auto swap = [&](int bit, void** slot, void* ext) {
+        if (!ext || *slot == ext) return;
+        if (!(pp.external & (1u << bit))) cudaFree(*slot);
+        *slot = ext;
+        pp.external |= 1u << bit;
+    };
+    swap(0, (void**)&pp.ids, v->ids);
+    swap(1, (void**)&pp.features, v->features);
+    swap(2, (void**)&pp.labels, v->labels);
+    swap(3, (void**)&pp.agg_src_off, v->agg_src);
+    swap(4, (void**)&pp.agg_dst_off, v->agg_dst);
+    swap(5, (void**)&pp.nc, v->node_counter);
+    swap(6, (void**)&pp.ec, v->edge_counter);
+    if (v->features && v->max_rows < c->max_rows) c->max_rows = v->max_rows;
+    if ((v->ids || v->agg_src || v->agg_dst) && v->capacity < c->capacity) c->capacity = v->capacity;   // kernels bound every id / edge write by it
+    invalidate_graphs(c);
     return LGN_OK;
 }
 

@@ -53,8 +53,8 @@ struct Pipe {
     int32_t* draw_key;         // hash layout: the node id read with the payload
     int32_t* tile_n;           // int32[max tiles of a hop]: valid draws (= edges) of the tile
     int32_t* tile_new;         // new unique nodes of the tile
-    int32_t* pre_e;            // exclusive prefixes of the two counts
-    int32_t* pre_n;
+    int32_t* super_e;          // sums of the two counts per 64 tiles
+    int32_t* super_n;
     unsigned long long batch_seq;   // batches started in this slot: generation = 62 - seq % 63
     BatchState* state;         // device
     int32_t* seed_stage;       // device staging for lgn_batch_from_host (ids | labels)
@@ -63,6 +63,7 @@ struct Pipe {
     cudaEvent_t ev_end;        // batch_end enqueued on the sampling stream
     cudaEvent_t ev_done;       // everything of the batch in this slot is complete
     bool pending;
+    uint32_t external;         // bit i set: wire buffer i (ids, features, labels, agg_src, agg_dst, nc, ec) is caller-owned (lgn_attach_buffers)
     cudaGraphExec_t graph_exec[2][2];   // [with_features][is_presc]: the captured RunOnce / RunPreSc DAG of this slot
     int graph_calls[2][2];
     cudaEvent_t ev_join;                // joins the gather branch back into the captured stream

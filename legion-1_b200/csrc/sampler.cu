@@ -15,15 +15,16 @@
 //              "generation | CAND | slot" into the node's dedup entry.  The valid draws of the tile are then
 //              compacted in slot order (shared-memory pass) into the tile's own region: later passes read
 //              e entries, not F*f slots.
-//   k_mark     probes each draw's entry once: winner <=> the entry still holds this draw's slot, i.e. it is the
-//              first occurrence of a node not seen in earlier hops.  Leaves the probed payload (and the key)
-//              next to the draw so the next pass needs no random access, one (edges, new nodes) count per
-//              tile, and the LAST CTA to finish turns the tile counts into exclusive prefixes and advances
-//              the batch counters (the reference's <<<1,1>>> update_counter).
-//   k_assign   tile by tile: edge index = prefix + position in the tile, winners are numbered by a ballot
-//              scan, appended to sampled_ids and published in their dedup entry; both local COO indices are
-//              written.  An in-hop duplicate whose winner is numbered by another thread stores -(handle+2);
-//              the next hop reads such an index through the dedup entry, k_batch_end patches what is left.
+//   k_mark     one warp per tile, 8 entries per lane in flight: probes each draw's entry once.  Winner <=> the entry
+//              still holds this draw's slot, i.e. it is the first occurrence of a node not seen in earlier hops.
+//              Leaves the probed payload (and the key) next to the draw so the next pass needs no random access,
+//              and (edges, new nodes) counts per tile and per 64 tiles.
+//   k_assign   one warp per tile: exclusive prefix from the per-64-tile sums + the tile counts of its own group (no
+//              device-wide scan, no look-back chain), edge index = prefix + position in the tile, winners numbered
+//              by ballot scans, appended to sampled_ids and published in their dedup entry; both local COO indices
+//              are written.  An in-hop duplicate whose winner is numbered by another thread stores -(handle+2);
+//              the next hop reads such an index through the dedup entry, k_batch_end patches what is left.  The
+//              warp of the last tile advances the batch counters (the reference's <<<1,1>>> update_counter).
 // Nothing is released at the end of a batch: dedup values carry a generation (common.cuh).
 #include "context.h"
 
@@ -32,7 +33,7 @@ namespace lgn {
 constexpr int SAMPLE_THREADS = 128;
 constexpr int SAMPLE_ITEMS = 32;     // frontier items per tile: small tiles => many CTAs even for hop 1 (B items)
 constexpr int SAMPLE_WARPS = SAMPLE_THREADS / 32;
-constexpr int SCAN_THREADS = 128;    // k_mark / k_assign CTA size (one tile per CTA iteration)
+constexpr int SCAN_THREADS = 128;    // k_mark / k_assign CTA size (one tile per WARP)
 
 // ------------------------------------------------------------------ batch begin
 __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__ src_ids,
@@ -67,7 +68,6 @@ __global__ void __launch_bounds__(256) k_batch_begin(const int32_t* __restrict__
         st->step = step;
         st->epoch = epoch;
         st->gen_base = gen_base;
-        st->done_ctr = 0;
     }
 }
 
@@ -77,7 +77,8 @@ template <int RNG, bool PRESC>
 __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant__ TopoView tv, const int32_t* __restrict__ ids,
                                                            const int32_t* __restrict__ agg_src_ids,
                                                            int32_t* __restrict__ draw_h, uint16_t* __restrict__ draw_s,
-                                                           int32_t* __restrict__ tile_n, const Dedup dd,
+                                                           int32_t* __restrict__ tile_n, int32_t* __restrict__ super_e,
+                                                           int32_t* __restrict__ super_n, const Dedup dd,
                                                            BatchState* __restrict__ st, int hop, int f,
                                                            unsigned long long seed, uint32_t* __restrict__ topo_hot,
                                                            long long n_nodes)
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
     // the grid is sized for the SMs, not for the worst-case frontier: CTAs stride over the item tiles
     // that actually exist (F is only known on the device)
     const int n_tiles = (F + SAMPLE_ITEMS - 1) / SAMPLE_ITEMS;
+    if (blockIdx.x == 0)      // per-supertile sums of the next pass start from zero
+        for (int i = t; i <= n_tiles / 64; i += SAMPLE_THREADS) { super_e[i] = 0; super_n[i] = 0; }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int item0 = tile * SAMPLE_ITEMS;
         if (t < SAMPLE_ITEMS) {   // phase 1: one thread per frontier item reads its adjacency descriptor once
@@ -216,96 +219,80 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
 }
 
 // ------------------------------------------------------------------ mark
-// pass 1 over the hop's valid draws: who won?  The last CTA to finish scans the per-tile counts.
+// pass 1 over the hop's valid draws: who won?  One WARP per tile (no block barriers), U entries per lane in flight.
+// Leaves one (edges, new nodes) count per tile and their sums per group of 64 tiles ("supertile"), so that pass 2 can
+// form any tile's exclusive prefix from ~(tiles/64 + 64) values instead of a device-wide scan.
+constexpr int SUPER = 64;
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_mark(const int32_t* __restrict__ draw_h, const uint16_t* __restrict__ draw_s,
                                                        int32_t* __restrict__ draw_v, int32_t* __restrict__ draw_key,
                                                        const int32_t* __restrict__ tile_n, int32_t* __restrict__ tile_new,
-                                                       int32_t* __restrict__ pre_e, int32_t* __restrict__ pre_n, const Dedup dd,
-                                                       BatchState* __restrict__ st, int hop, int f,
-                                                       int32_t* __restrict__ nc, int32_t* __restrict__ ec, long long capacity)
+                                                       int32_t* __restrict__ super_e, int32_t* __restrict__ super_n, const Dedup dd,
+                                                       const BatchState* __restrict__ st, int hop, int f)
 {
-    __shared__ int32_t s_red[SCAN_THREADS / 32];
-    __shared__ int32_t s_scan[2][SCAN_THREADS];
-    __shared__ bool s_last;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const HopState hs = st->hop[hop];
-    const int F = hs.n_items;
+    constexpr int U = 8;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * SCAN_THREADS) >> 5;
+    const int F = st->hop[hop].n_items;
     const int n_tiles = (F + SAMPLE_ITEMS - 1) / SAMPLE_ITEMS;
     const int TS = SAMPLE_ITEMS * f;
     const unsigned long long keep = policy_evict_last();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = warp; tile < n_tiles; tile += n_warps) {
         const int n = tile_n[tile];
         const long long base = (long long)tile * TS;
         int wins = 0;
-        for (int j = t; j < n; j += SCAN_THREADS) {
-            const int32_t h = draw_h[base + j];
-            int32_t key;
-            const int32_t pv = dedup_payload_key(dd, h, key, keep);
-            draw_v[base + j] = pv;
-            if (dd.bits) draw_key[base + j] = key;
-            wins += pv == (CAND | (int32_t)(base + draw_s[base + j])) ? 1 : 0;
+        for (int j0 = 0; j0 < n; j0 += 32 * U) {
+            int32_t h[U], pv[U], key[U];
+            int s[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = j0 + 32 * u + lane;
+                h[u] = j < n ? draw_h[base + j] : -1;
+                s[u] = j < n ? (int)draw_s[base + j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) { key[u] = -1; pv[u] = 0; if (h[u] >= 0) pv[u] = dedup_payload_key(dd, h[u], key[u], keep); }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (h[u] >= 0) {
+                    draw_v[base + j] = pv[u];
+                    if (dd.bits) draw_key[base + j] = key[u];
+                    wins += pv[u] == (CAND | (int32_t)(base + s[u])) ? 1 : 0;
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wins += __shfl_xor_sync(0xffffffffu, wins, o);
-        if (lane == 0) s_red[warp] = wins;
-        __syncthreads();
-        if (t == 0) {
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < SCAN_THREADS / 32; w++) tot += s_red[w];
-            tile_new[tile] = tot;
+        if (lane == 0) {
+            tile_new[tile] = wins;
+            if (n) atomicAdd(&super_e[tile / SUPER], n);
+            if (wins) atomicAdd(&super_n[tile / SUPER], wins);
         }
-        __syncthreads();
-    }
-    // last CTA done: exclusive prefixes over the tiles + counters (update_counter(op 2/4), Kernels.cu:128-149, any hop)
-    __threadfence();
-    if (t == 0) s_last = atomicAdd(&st->done_ctr, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int chunk = (n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int lo = min(n_tiles, t * chunk), hi = min(n_tiles, lo + chunk);
-    int se = 0, sn = 0;
-    for (int i = lo; i < hi; i++) { se += __ldcg(tile_n + i); sn += __ldcg(tile_new + i); }
-    s_scan[0][t] = se; s_scan[1][t] = sn;
-    __syncthreads();
-    int be = 0, bn = 0, te = 0, tn = 0;
-    for (int i = 0; i < SCAN_THREADS; i++) {
-        const int a = s_scan[0][i], b = s_scan[1][i];
-        if (i < t) { be += a; bn += b; }
-        te += a; tn += b;
-    }
-    for (int i = lo; i < hi; i++) {
-        pre_e[i] = be; pre_n[i] = bn;
-        be += __ldcg(tile_n + i); bn += __ldcg(tile_new + i);
-    }
-    if (t == 0) {
-        HopState nx;
-        nx.n_items = te; nx.item_base = hs.edge_base; nx.node_base = hs.node_base + tn; nx.edge_base = hs.edge_base + te;
-        st->hop[hop + 1] = nx;
-        st->tot_items += (unsigned long long)hs.n_items;
-        st->tot_edges += (unsigned long long)te;
-        if ((long long)nx.node_base > capacity || (long long)nx.edge_base > capacity) st->status = LGN_E_CAPACITY;
-        nc[0] = nx.node_base; nc[1] = 0; nc[2] = te;
-        nc[5 + 2 * hop] = hs.node_base; nc[6 + 2 * hop] = tn;
-        if (7 + 2 * hop < 16) nc[7 + 2 * hop] = nx.node_base;
-        ec[0] = nx.edge_base; ec[1] = 0; ec[2] = hs.edge_base; ec[3 + hop] = nx.edge_base;
-        st->done_ctr = 0;
     }
 }
 
 // ------------------------------------------------------------------ assign
-// pass 2: edge index = tile prefix + position, winners numbered by a ballot scan; both COO index arrays written.
-// k_mark's scan leaves hop[hop] as it was (it writes hop[hop + 1]).
+// pass 2, one warp per tile: edge index = tile prefix + position, winners numbered by ballot scans; both COO index
+// arrays written.  The warp that owns the LAST tile advances the counters (update_counter(op 2/4), Kernels.cu:128-149).
+__device__ __forceinline__ int warp_sum(int x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_assign(
     const int32_t* __restrict__ draw_h, const uint16_t* __restrict__ draw_s, const int32_t* __restrict__ draw_v,
-    const int32_t* __restrict__ draw_key, const int32_t* __restrict__ tile_n, const int32_t* __restrict__ pre_e,
-    const int32_t* __restrict__ pre_n, int32_t* __restrict__ ids, int32_t* __restrict__ agg_src_ids,
-    int32_t* __restrict__ agg_dst_ids, int32_t* __restrict__ agg_src_off, int32_t* __restrict__ agg_dst_off, const Dedup dd,
-    const int32_t* __restrict__ seed_h, const BatchState* __restrict__ st, int hop, int f, long long capacity)
+    const int32_t* __restrict__ draw_key, const int32_t* __restrict__ tile_n, const int32_t* __restrict__ tile_new,
+    const int32_t* __restrict__ super_e, const int32_t* __restrict__ super_n, int32_t* __restrict__ ids,
+    int32_t* __restrict__ agg_src_ids, int32_t* __restrict__ agg_dst_ids, int32_t* __restrict__ agg_src_off,
+    int32_t* __restrict__ agg_dst_off, const Dedup dd, const int32_t* __restrict__ seed_h, int32_t* __restrict__ nc,
+    int32_t* __restrict__ ec, BatchState* __restrict__ st, int hop, int f, long long capacity)
 {
-    __shared__ int32_t s_w[SCAN_THREADS / 32];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * SCAN_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * SCAN_THREADS) >> 5;
     const HopState hs = st->hop[hop];
     const int F = hs.n_items;
     const int n_tiles = (F + SAMPLE_ITEMS - 1) / SAMPLE_ITEMS;
@@ -313,64 +300,93 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_assign(
     const int32_t gen_base = st->gen_base;
     const int32_t* frontier = hop == 0 ? ids : agg_src_ids + hs.item_base;
     const unsigned long long keep = policy_evict_last();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int n = tile_n[tile];
+    // an empty frontier has no last tile: warp 0 advances the counters
+    const int tile_end = n_tiles > 0 ? n_tiles : 1;
+    for (int tile = warp; tile < tile_end; tile += n_warps) {
+        // exclusive prefix of (edges, new nodes) before this tile: whole supertiles, then the tiles of its own supertile
+        int pe = 0, pn = 0;
+        const int sup = tile / SUPER;
+        for (int i = lane; i < sup; i += 32) { pe += super_e[i]; pn += super_n[i]; }
+        for (int i = sup * SUPER + lane; i < tile; i += 32) { pe += tile_n[i]; pn += tile_new[i]; }
+        pe = warp_sum(pe); pn = warp_sum(pn);
+        const int n = n_tiles > 0 ? tile_n[tile] : 0;
         const long long base = (long long)tile * TS;
-        const long long e0 = (long long)hs.edge_base + pre_e[tile];
-        long long p0 = (long long)hs.node_base + pre_n[tile];
-        for (int j0 = 0; j0 < n; j0 += SCAN_THREADS) {
-            const int j = j0 + t;
-            const bool valid = j < n;
-            int32_t h = -1, pv = 0, key = -1, s = 0;
-            if (valid) {
-                h = draw_h[base + j]; pv = draw_v[base + j]; s = draw_s[base + j];
-                key = dd.bits ? draw_key[base + j] : h;
-            }
-            const bool win = valid && pv == (CAND | (int32_t)(base + s));
-            const uint32_t m = __ballot_sync(0xffffffffu, win);
-            if (lane == 0) s_w[warp] = __popc(m);
-            __syncthreads();
-            int rank = __popc(m & ((1u << lane) - 1u)), chunk_new = 0;
+        const long long e0 = (long long)hs.edge_base + pe;
+        long long p0 = (long long)hs.node_base + pn;
+        for (int j0 = 0; j0 < n; j0 += 32 * U) {
+            int32_t h[U], pv[U], key[U], src[U], dst_off[U];
+            int s[U], rank[U];
+            bool win[U];
 #pragma unroll
-            for (int w = 0; w < SCAN_THREADS / 32; w++) {
-                if (w < warp) rank += s_w[w];
-                chunk_new += s_w[w];
-            }
-            if (valid) {
-                const int item = tile * SAMPLE_ITEMS + s / f;
-                const int32_t src = frontier[item];
-                // local index of the frontier node: a seed's index sits in its dedup entry; a later hop's item is the previous
-                // hop's edge, already relabelled (construct_graph, Kernels.cu:458-461) unless its winner was numbered by
-                // another thread: then the entry -(handle+2) points at the dedup entry that holds the index by now
-                int32_t dst_off;
-                if (hop == 0) {
-                    const int32_t sh = dd.bits ? seed_h[item] : src;   // a seed whose claim found the hash table full has no handle
-                    dst_off = sh >= 0 ? dedup_payload(dd, sh, keep) : item;
-                } else {
-                    dst_off = agg_src_off[hs.item_base + item];
-                    if (dst_off < 0) dst_off = dedup_payload(dd, -2 - dst_off, keep);
+            for (int u = 0; u < U; u++) {
+                const int j = j0 + 32 * u + lane;
+                h[u] = -1; pv[u] = 0; s[u] = 0; key[u] = -1;
+                if (j < n) {
+                    h[u] = draw_h[base + j]; pv[u] = draw_v[base + j]; s[u] = draw_s[base + j];
+                    key[u] = dd.bits ? draw_key[base + j] : h[u];
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {   // frontier node of the draw and its local index
+                src[u] = -1; dst_off[u] = 0;
+                if (h[u] >= 0) {
+                    const int item = tile * SAMPLE_ITEMS + s[u] / f;
+                    src[u] = frontier[item];
+                    // a seed's index sits in its dedup entry; a later hop's item is the previous hop's edge, already relabelled
+                    // (construct_graph, Kernels.cu:458-461) unless its winner was numbered by another thread: then the entry
+                    // -(handle+2) points at the dedup entry that holds the index by now
+                    if (hop == 0) dst_off[u] = dd.bits ? seed_h[item] : src[u];      // handle of the seed (hash: -1 if the table was full)
+                    else dst_off[u] = agg_src_off[hs.item_base + item];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (h[u] >= 0) {
+                    const int item = tile * SAMPLE_ITEMS + s[u] / f;
+                    if (hop == 0) dst_off[u] = dst_off[u] >= 0 ? dedup_payload(dd, dst_off[u], keep) : item;
+                    else if (dst_off[u] < 0) dst_off[u] = dedup_payload(dd, -2 - dst_off[u], keep);
+                }
+                win[u] = h[u] >= 0 && pv[u] == (CAND | (int32_t)(base + s[u]));
+                const uint32_t m = __ballot_sync(0xffffffffu, win[u]);
+                rank[u] = (int)(p0 - ((long long)hs.node_base + pn)) + __popc(m & ((1u << lane) - 1u));
+                p0 += __popc(m);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (h[u] < 0) continue;
+                const int j = j0 + 32 * u + lane;
                 int32_t src_off;
-                if (win) {                       // Kernels.cu:418-438
-                    const long long pos = p0 + rank;
+                if (win[u]) {                       // Kernels.cu:418-438
+                    const long long pos = (long long)hs.node_base + pn + rank[u];
                     if (pos < capacity) {
-                        ids[pos] = key;
-                        dedup_publish(dd, h, key, gen_base | (int32_t)pos, keep);
+                        ids[pos] = key[u];
+                        dedup_publish(dd, h[u], key[u], gen_base | (int32_t)pos, keep);
                     }
                     src_off = (int32_t)pos;
                 } else {
-                    src_off = pv < CAND ? pv : -2 - h;   // winner of this hop numbered elsewhere: read it through the entry later
+                    src_off = pv[u] < CAND ? pv[u] : -2 - h[u];   // winner of this hop numbered elsewhere: read it through the entry later
                 }
                 const long long e = e0 + j;
                 if (e < capacity) {                    // Kernels.cu:423-424, 441-445
-                    agg_src_ids[e] = key;
-                    agg_dst_ids[e] = src;
+                    agg_src_ids[e] = key[u];
+                    agg_dst_ids[e] = src[u];
                     agg_src_off[e] = src_off;
-                    agg_dst_off[e] = dst_off;
+                    agg_dst_off[e] = dst_off[u];
                 }
             }
-            p0 += chunk_new;
-            __syncthreads();
+        }
+        if (tile == tile_end - 1 && lane == 0) {
+            const int te = pe + n, tn = (int)(p0 - (long long)hs.node_base);
+            HopState nx;
+            nx.n_items = te; nx.item_base = hs.edge_base; nx.node_base = hs.node_base + tn; nx.edge_base = hs.edge_base + te;
+            st->hop[hop + 1] = nx;
+            st->tot_items += (unsigned long long)hs.n_items;
+            st->tot_edges += (unsigned long long)te;
+            if ((long long)nx.node_base > capacity || (long long)nx.edge_base > capacity) st->status = LGN_E_CAPACITY;
+            nc[0] = nx.node_base; nc[1] = 0; nc[2] = te;
+            nc[5 + 2 * hop] = hs.node_base; nc[6 + 2 * hop] = tn;
+            if (7 + 2 * hop < 16) nc[7 + 2 * hop] = nx.node_base;
+            ec[0] = nx.edge_base; ec[1] = 0; ec[2] = hs.edge_base; ec[3 + hop] = nx.edge_base;
         }
     }
 }
@@ -383,12 +399,26 @@ __global__ void __launch_bounds__(256) k_batch_end(const int32_t* __restrict__ i
                                                    int32_t* __restrict__ agg_src_off)
 {
     // in-hop duplicates numbered by another thread: the index is in the node's dedup entry (construct_graph's second
-    // lookup, Kernels.cu:458)
+    // lookup, Kernels.cu:458).  Four edges per thread and iteration: one 16-byte load, the (rare) probes of all four in
+    // flight together, only patched entries written back.
     const int n_edges = st->hop[n_hops].edge_base;
     const unsigned long long keep = policy_evict_last();
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
-        const int32_t so = agg_src_off[e];
-        if (so < 0) agg_src_off[e] = dedup_payload(dd, -2 - so, keep);
+    const int n_quads = (n_edges + 3) >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
+        const int e = q << 2;
+        int32_t so[4];
+        if (e + 3 < n_edges) {
+            const int4 v = *reinterpret_cast<const int4*>(agg_src_off + e);
+            so[0] = v.x; so[1] = v.y; so[2] = v.z; so[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) so[k] = e + k < n_edges ? agg_src_off[e + k] : 0;
+        }
+        int32_t fix[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) fix[k] = so[k] < 0 ? dedup_payload(dd, -2 - so[k], keep) : so[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (so[k] < 0) agg_src_off[e + k] = fix[k];
     }
     if (PRESC) {
         const int total = st->hop[n_hops].node_base;   // nc[9] for two hops
@@ -430,18 +460,19 @@ void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc)
     if (sblocks > c->n_sm * c->sample_ctas_per_sm) sblocks = c->n_sm * c->sample_ctas_per_sm;
     const size_t smem = (size_t)SAMPLE_ITEMS * f * sizeof(int32_t);     // <= 32 KB (f <= 256)
 #define LGN_SAMPLE(R, P)                                                                                                  \
-    k_sample<R, P><<<sblocks, SAMPLE_THREADS, smem, s>>>(c->topo, p.ids, p.agg_src_ids, p.draw_h, p.draw_s, p.tile_n, p.dedup, \
+    k_sample<R, P><<<sblocks, SAMPLE_THREADS, smem, s>>>(c->topo, p.ids, p.agg_src_ids, p.draw_h, p.draw_s, p.tile_n, p.super_e, p.super_n, p.dedup, \
                                                          p.state, hop, f, c->cfg.rng_seed, c->topo_hotness, c->cfg.n_nodes)
     if (c->cfg.rng_mode == LGN_RNG_MINSTD) { if (presc) LGN_SAMPLE(LGN_RNG_MINSTD, true); else LGN_SAMPLE(LGN_RNG_MINSTD, false); }
     else { if (presc) LGN_SAMPLE(LGN_RNG_PHILOX, true); else LGN_SAMPLE(LGN_RNG_PHILOX, false); }
 #undef LGN_SAMPLE
-    int rblocks = tiles_max;
+    int rblocks = cdiv(tiles_max, SCAN_THREADS / 32);      // one warp per tile
     if (rblocks > c->n_sm * c->resolve_ctas_per_sm) rblocks = c->n_sm * c->resolve_ctas_per_sm;
     if (rblocks < 1) rblocks = 1;
-    k_mark<<<rblocks, SCAN_THREADS, 0, s>>>(p.draw_h, p.draw_s, p.draw_v, p.draw_key, p.tile_n, p.tile_new, p.pre_e, p.pre_n, p.dedup,
-                                            p.state, hop, f, p.nc, p.ec, c->capacity);
-    k_assign<<<rblocks, SCAN_THREADS, 0, s>>>(p.draw_h, p.draw_s, p.draw_v, p.draw_key, p.tile_n, p.pre_e, p.pre_n, p.ids, p.agg_src_ids,
-                                              p.agg_dst_ids, p.agg_src_off, p.agg_dst_off, p.dedup, p.seed_h, p.state, hop, f, c->capacity);
+    k_mark<<<rblocks, SCAN_THREADS, 0, s>>>(p.draw_h, p.draw_s, p.draw_v, p.draw_key, p.tile_n, p.tile_new, p.super_e, p.super_n, p.dedup,
+                                            p.state, hop, f);
+    k_assign<<<rblocks, SCAN_THREADS, 0, s>>>(p.draw_h, p.draw_s, p.draw_v, p.draw_key, p.tile_n, p.tile_new, p.super_e, p.super_n, p.ids,
+                                              p.agg_src_ids, p.agg_dst_ids, p.agg_src_off, p.agg_dst_off, p.dedup, p.seed_h, p.nc, p.ec,
+                                              p.state, hop, f, c->capacity);
 }
 
 void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc)

@@ -1,7 +1,7 @@
 """The reference's OWN trainers, unchanged, against this repo's server: `legion` (server.cpp over the C-ABI) in one
 process, the reference's `ipc_service` torch extension built UNMODIFIED from /root/reference/pytorch_extension
 (oracle/ref_ext/build_ext.py -> oracle/_ref/ext/) and its byte-compiled, unedited legion_graphsage.py /
-legion_gcn.py (oracle/_ref/trainers/*.pyc) in another, DGL / torchmetrics provided by the stand-ins under
+legion_gcn.py (oracle/_ref/trainers/*.bin) in another, DGL / torchmetrics provided by the stand-ins under
 legion-1_b200/shims (neither is installed here).  Proves the wire format (shm layout, semaphore protocol, CUDA IPC
 handles, counter slots) against the consumer it was written for: ipc_cuda_kernel.cu:38-230, ipc_service.cpp:43-93,
 legion_graphsage.py:72-89,149-168."""
@@ -22,7 +22,7 @@ SHIMS = os.path.join(ROOT, "legion-1_b200", "shims")
 
 
 def _have_reference_build():
-    return bool(glob.glob(os.path.join(EXT_DIR, "ipc_service*.so"))) and os.path.exists(os.path.join(TRAINERS, "legion_graphsage.pyc"))
+    return bool(glob.glob(os.path.join(EXT_DIR, "ipc_service*.so"))) and os.path.exists(os.path.join(TRAINERS, "legion_graphsage.bin"))
 
 
 @pytest.mark.parametrize("trainer", ["legion_graphsage", "legion_gcn"])
@@ -45,7 +45,7 @@ def test_unchanged_reference_trainer_runs_against_the_server(tmp_path, trainer):
     try:
         env = dict(os.environ, PYTHONPATH=os.pathsep.join([EXT_DIR, SHIMS, os.environ.get("PYTHONPATH", "")]))
         env.pop("MASTER_ADDR", None); env.pop("MASTER_PORT", None)
-        out = subprocess.run([sys.executable, os.path.join(TRAINERS, trainer + ".pyc"), "--class_num", str(cfg["n_class"]),
+        out = subprocess.run([sys.executable, os.path.join(TRAINERS, trainer + ".bin"), "--class_num", str(cfg["n_class"]),
                               "--features_num", str(cfg["dim"]), "--train_batch_size", str(B), "--hidden_dim", "32",
                               "--epoch", str(epochs), "--gpu_num", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=work)
         assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

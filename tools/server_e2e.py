@@ -61,6 +61,9 @@ def main():
     ap.add_argument("--cache-gb", type=float, default=38.0)
     ap.add_argument("--dir", default="/dev/shm/lgn_e2e")
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--trainer", default="", help="legion_graphsage | legion_gcn: consume with the reference's UNCHANGED trainer "
+                    "(oracle/_ref/trainers/*.bin + its own ipc_service extension, oracle/_ref/ext) and report the epoch times it prints")
+    ap.add_argument("--rng", default="philox")
     ap.add_argument("--client", type=int, default=-1)
     ap.add_argument("--dim", type=int, default=0)
     a = ap.parse_args()
@@ -93,7 +96,7 @@ def main():
     del host
     t_gen = time.perf_counter() - t0
 
-    env = dict(os.environ, LEGION_RNG="philox", LEGION_FANOUT=",".join(map(str, cfg["fanout"])), E2E_EPOCHS=str(a.epochs),
+    env = dict(os.environ, LEGION_RNG=a.rng, LEGION_FANOUT=",".join(map(str, cfg["fanout"])), E2E_EPOCHS=str(a.epochs),
                E2E_HOPS=str(len(cfg["fanout"])))
     log = open(os.path.join(a.dir, "server.log"), "w")
     t0 = time.perf_counter()
@@ -106,6 +109,28 @@ def main():
                 break
             time.sleep(0.5)
         t_ready = time.perf_counter() - t0
+        if a.trainer:      # the reference's own trainer, unchanged, one process per GPU through its mp.spawn
+            ref = os.path.join(ROOT, "oracle", "_ref")
+            tenv = dict(env, PYTHONPATH=os.pathsep.join([os.path.join(ref, "ext"), os.path.join(ROOT, "legion-1_b200", "shims"), env.get("PYTHONPATH", "")]))
+            tenv.pop("MASTER_ADDR", None); tenv.pop("MASTER_PORT", None)
+            t1 = time.perf_counter()
+            out = subprocess.run([sys.executable, os.path.join(ref, "trainers", a.trainer + ".bin"), "--class_num", str(cfg["n_class"]),
+                                  "--features_num", str(D), "--train_batch_size", str(B), "--hidden_dim", "256", "--epoch", str(a.epochs),
+                                  "--gpu_num", str(a.gpus)], env=tenv, cwd=a.dir, capture_output=True, text=True, timeout=1800)
+            wall = time.perf_counter() - t1
+            if out.returncode != 0:
+                raise RuntimeError("trainer failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+            srv.wait(timeout=120)
+            import re
+            costs = [float(x) for x in re.findall(r"Epoch:\d+, Cost:([0-9.eE+-]+) s", out.stdout)]
+            steps = [int(x) for x in re.findall(r"Train Steps: (\d+)", open(os.path.join(a.dir, "server.log")).read())]
+            print(json.dumps({"what": "legion server binary -> the reference's unchanged %s.py through its unmodified ipc_service extension" % a.trainer,
+                              "n_gpus": a.gpus, "workload": f"{a.config} shape, {N} nodes, {n_edges} edges, {D}-d, batch {B}/GPU, fanout {cfg['fanout']}, agg mode {a.agg_mode}, rng {a.rng}",
+                              "graphsage_epoch_s": costs, "train_steps_per_epoch": steps[0] if steps else None, "trainer_wall_s": wall,
+                              "model": "the trainer's own: 2 x SAGEConv/GraphConv hidden 256 (DGL stand-in), Adam, DDP over NCCL",
+                              "trainer_stdout_tail": out.stdout[-400:], "server_load_presample_cache_s": t_ready}))
+            shutil.rmtree(a.dir, ignore_errors=True)
+            return
         cl = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--client", str(d), "--dim", str(D), "--warmup", str(a.warmup)],
                                env=env, stdout=subprocess.PIPE, text=True) for d in range(a.gpus)]
         res = []
