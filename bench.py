@@ -85,30 +85,49 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  nvidia-smi needs ~100 ms to
+    deliver its first line, so it is started early and every line is stamped on arrival; only the lines that arrived
+    between begin() and end() -- the timed passes -- are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, dev):
         self.dev, self.proc, self.lines = dev, None, []
+        self.t0 = self.t1 = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         self.t.join(timeout=2)
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.perf_counter()) + 0.03      # a line describes the 20 ms before it arrived
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1]
+        note = None
+        if not inside and self.lines:       # region shorter than the sampling period: the line nearest to it
+            near = min(self.lines, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))
+            inside, note = [near[1]], "timed region shorter than the 20 ms sampling period: nearest sample"
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -119,8 +138,11 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def workload(args):
@@ -766,6 +788,8 @@ def run_b200(args):
         return probe_mode(L, r, dist, world, rank, c, lp, lanes, stream, sp, NL, B, D, train_steps, barrier, step_resident)
 
     # ======================= primary placement ==============================================
+    clocks = ClockSampler(local)
+    clocks.start()
     c = build_cache(args.placement)
     parity = None
     if not args.no_parity:
@@ -773,16 +797,14 @@ def run_b200(args):
         parity = parity_check(c)
         parity["seconds"] = time.perf_counter() - t0
     r.set_epoch(1)                                    # the timed epoch is not the presampled one
-    clocks = ClockSampler(local)
     r.tier_counts(reset=True, stream=sp)
-    clocks.start()
+    clocks.begin()
     ms_prof, prof = timed(step_resident, K, W, profile=True)      # instrumented pass: per-operator CUDA events, eager launches
     host_enqueue_ms = host_ms[0]
     tiers = r.tier_counts(reset=True, stream=sp)
     ms_total, _ = timed(step_resident, K, W)          # THE timed region: the same K steps as the product runs them (CUDA-graph replay)
     host_enqueue_plain_ms = host_ms[0]
     ms_e2e, _ = timed(step_e2e, K, W)
-    clk = clocks.stop()                               # nvidia-smi samples span the three timed passes (each only a few ms long)
     edges, rows, hop_items, hop_edges, hop_new = count_work(K, W)
     tot = torch.tensor([edges, rows], device=rdev, dtype=torch.float64)
     if world > 1:
@@ -798,6 +820,8 @@ def run_b200(args):
     ms_long = None
     if long_K > 0:
         ms_long, _ = timed(step_resident, long_K, W)
+    clocks.end()                                      # samples span the three timed passes and the long run of the same region
+    clk = clocks.stop()
 
     # ---- the dominant kernel timed ALONE (no other batch in flight) ------------------------
     alone_ms = alone_calls = alone_rows = 0

@@ -30,6 +30,8 @@ struct RefCtx {
     GPUCache* cache;
     GPUMemoryPool* pool;
     cudaStream_t stream;
+    cudaStream_t stream2;          // the reference runner's second stream (feature extraction, Server.cu:176-207)
+    cudaEvent_t ev[8];
     int32_t* ids[2]; int32_t* labels[2]; int32_t* src_off[2]; int32_t* dst_off[2]; int32_t* nc[2]; int32_t* ec[2];
     float* feats[2];
     int64_t num_ids;
@@ -83,6 +85,8 @@ extern "C" RefCtx* ref_create(const int64_t* indptr, const int32_t* indices, int
     c->cache->Initialize(cache_memory, 0, dim, c->train_step, 1);
     c->n_nodes = n_nodes; c->dim = dim; c->batch = batch; c->f1 = f1; c->f2 = f2; c->pipe = 0;
     cudaStreamCreate(&c->stream);
+    cudaStreamCreate(&c->stream2);
+    for (int i = 0; i < 8; i++) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
 
     // GPURunner::Initialize, Server.cu:183-246
     c->num_ids = (int64_t)batch * (1 + f1 + (int64_t)f1 * f2);
@@ -204,14 +208,28 @@ extern "C" void ref_time_batches(RefCtx* c, int32_t first_iter, int32_t n, doubl
         const int iter = first_iter + i;
         c->pool->SetCurrentMode(0);
         c->pool->SetIter(iter % (c->train_step > 0 ? c->train_step : 1));
-        batch_generator_kernel(c->stream, c->node, c->cache, c->pool, c->batch, iter % (c->train_step > 0 ? c->train_step : 1), 0, 0, 0);
-        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 1, true);
-        GPU_Random_Sampling(c->stream, c->graph, c->cache, c->pool, c->f1, 2, false);
-        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 3, true);
-        GPU_Random_Sampling(c->stream, c->graph, c->cache, c->pool, c->f2, 4, false);
-        get_feature_kernel(c->stream, c->cache, c->node, c->pool, 0, 5, true);
-        make_update_plan(c->stream, c->graph, c->cache, c->pool, 0, 0);
-        cudaStreamSynchronize(c->stream);          // Server.cu:318-323 busy-polls the last event before the next batch
+        // GPURunner::RunOnce (Server.cu:310-323): operator i runs on stream i % 2, an odd operator (feature extraction,
+        // cache update) first makes stream 1 wait for the event of operator i - 1; the batch is complete when the last
+        // operator's event has fired (the reference busy-polls it before it touches the next batch)
+        cudaStream_t s0 = c->stream, s1 = c->stream2;
+        batch_generator_kernel(s0, c->node, c->cache, c->pool, c->batch, iter % (c->train_step > 0 ? c->train_step : 1), 0, 0, 0);
+        cudaEventRecord(c->ev[0], s0);
+        cudaStreamWaitEvent(s1, c->ev[0], 0);
+        get_feature_kernel(s1, c->cache, c->node, c->pool, 0, 1, true);
+        GPU_Random_Sampling(s0, c->graph, c->cache, c->pool, c->f1, 2, false);
+        cudaEventRecord(c->ev[2], s0);
+        cudaStreamWaitEvent(s1, c->ev[2], 0);
+        get_feature_kernel(s1, c->cache, c->node, c->pool, 0, 3, true);
+        GPU_Random_Sampling(s0, c->graph, c->cache, c->pool, c->f2, 4, false);
+        cudaEventRecord(c->ev[4], s0);
+        cudaStreamWaitEvent(s1, c->ev[4], 0);
+        get_feature_kernel(s1, c->cache, c->node, c->pool, 0, 5, true);
+        make_update_plan(s0, c->graph, c->cache, c->pool, 0, 0);
+        cudaEventRecord(c->ev[6], s0);
+        cudaStreamWaitEvent(s1, c->ev[6], 0);
+        update_cache(s1, c->cache, c->node, c->pool, 0, 0);
+        cudaEventRecord(c->ev[7], s1);
+        cudaEventSynchronize(c->ev[7]);
         c->pipe ^= 1;
         c->pool->SetCurrentPipe(c->pipe);
     }
