@@ -163,13 +163,13 @@ const char* lgn_gather_kernel_name(const lgn_ctx* ctx);
 /* op 6/7: make_update_plan / update_cache (Kernels.cu:759-805): node hotness when
  * is_presc (HotnessMeasure, GPUCache.cu:227-235) and scratch reset (ClearPosMap). */
 int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);
-/* the whole GPURunner::RunOnce / RunPreSc DAG (Server.cu:284-328) on one stream pair:
- * sampling on `stream`, gathers on the context's second stream, joined at the end. */
-int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_presc);
-/* lgn_run_batch does not join the two streams: the next batch's sampling overlaps this batch's
- * gathers (pipeline depth 2).  A slot's batch is complete when its event fires:
+/* the whole GPURunner::RunOnce / RunPreSc DAG (Server.cu:284-328) of the selected slot: sampling on `stream`, feature
+ * extraction on the slot's own low-priority stream, event-chained per hop.  Replayed as a CUDA graph from the second
+ * call on.  `stream` is NOT joined with the gather stream at the end: the next batch's sampling overlaps this
+ * batch's gathers.  A slot's batch is complete when its event fires:
  * lgn_wait_pipe makes `stream` wait for it (device side), lgn_sync_pipe blocks the host
  * (the reference's busy-poll on the last operator event, Server.cu:318-323). */
+int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_presc);
 /* operator-by-operator calls act on the slot chosen by the last batch_generate / select */
 int lgn_select_pipe(lgn_ctx* ctx, int32_t pipe);
 int lgn_wait_pipe(lgn_ctx* ctx, void* stream, int32_t pipe);
@@ -186,7 +186,7 @@ typedef struct {
     int32_t* agg_dst;       /* int32[capacity]   local index of frontier node     (IPC handle 4) */
     int32_t* node_counter;  /* int32[16]                      (IPC handle 5) */
     int32_t* edge_counter;  /* int32[16]                      (IPC handle 6) */
-    int32_t* agg_src_ids;   /* raw ids (GPUMemoryPool::GetAggSrcId), shared between pipes */
+    int32_t* agg_src_ids;   /* raw ids (GPUMemoryPool::GetAggSrcId); one array per slot here (the reference shares one) */
     int32_t* agg_dst_ids;   /* raw ids (GPUMemoryPool::GetAggDstId) */
     int64_t capacity;
     int64_t max_rows;

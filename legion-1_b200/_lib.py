@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "_build", "liblegion_b200.so")
+SO_PATH = os.environ.get("LGN_LIBRARY") or os.path.join(_HERE, "_build", "liblegion_b200.so")      # LGN_LIBRARY: the debug build
 HEADER = os.path.join(ROOT, "include", "legion_b200.h")
 
 MAX_HOPS, MAX_PARTS, PIPELINE_DEPTH = 5, 8, 2
@@ -43,7 +43,7 @@ class Steps(C.Structure):
 
 def build(verbose=False):
     """compile liblegion_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8", "all", "debug"], capture_output=True, text=True)
     if verbose or out.returncode:
         print(out.stdout[-4000:], out.stderr[-4000:])
     if out.returncode:

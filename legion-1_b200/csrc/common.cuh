@@ -5,6 +5,16 @@
 
 #include "../../include/legion_b200.h"
 
+// Debug build (`make -C legion-1_b200/csrc debug` -> _build/liblegion_b200_dbg.so, -DLGN_DEBUG): a device-side assert
+// in front of every indexed write of the sampling kernels.  compute-sanitizer is closed on the measurement pool;
+// the parity suite run against this build (LGN_LIBRARY=<path> pytest -m gpu) is the out-of-bounds check.
+#ifdef LGN_DEBUG
+#include <assert.h>
+#define LGN_ASSERT(c) assert(c)
+#else
+#define LGN_ASSERT(c) ((void)0)
+#endif
+
 namespace lgn {
 
 // ---- dedup value encoding ------------------------------------------------
@@ -41,7 +51,8 @@ struct BatchState {
     uint32_t epoch;         // philox counter word 1
     int32_t gen_base;       // generation of this batch << GEN_SHIFT (dedup values, see above)
     uint32_t pad1;
-    int32_t pad2[2];
+    int32_t dbg_max_slots;  // bounds the debug build asserts against (slots of the widest hop, id / edge capacity)
+    int32_t dbg_capacity;
     unsigned long long tier_rows[4];   // local, peer, host rows gathered
     unsigned long long tot_items;      // frontier items expanded since the last reset (every hop)
     unsigned long long tot_edges;      // edges sampled since the last reset

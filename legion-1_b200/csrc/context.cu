@@ -247,6 +247,10 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         CK(malloc_pages(&pp.super_n, (c->max_tiles / 64 + 2) * sizeof(int32_t)));
         CK(malloc_pages(&pp.state, sizeof(lgn::BatchState)));
         CK(cudaMemset(pp.state, 0, sizeof(lgn::BatchState)));
+        {
+            const int32_t dbg[2] = {(int32_t)(max_slots + 16), (int32_t)cap};
+            CK(cudaMemcpy(&pp.state->dbg_max_slots, dbg, sizeof(dbg), cudaMemcpyHostToDevice));
+        }
         CK(malloc_pages(&pp.seed_stage, (size_t)cfg->batch_size * 2 * sizeof(int32_t)));
         if (!c->dedup_hash) {
             int rc = fill_i32(pp.slot_map, lgn::EMPTY, cfg->n_nodes, 0);

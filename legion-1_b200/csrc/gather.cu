@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_con
                              : "=r"(done) : "r"(my_bar), "r"(phase) : "memory");
             }
             phase ^= 1u;
+            LGN_ASSERT((long long)(off + r) < max_rows);
             float* dst = out + (long long)(off + r) * dim;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                          ::"l"(dst), "r"(my_buf), "r"(row_bytes), "l"(stream_pol) : "memory");

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
                         if (h < 0) st->status = LGN_E_CAPACITY;
                         else if (PRESC) atomicAdd(&s_cnt[il[u]], 1);
                     }
+                    LGN_ASSERT(s < SAMPLE_ITEMS * f);
                     s_val[s] = h;
                 }
             }
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const __grid_constant
             const uint32_t m = __ballot_sync(0xffffffffu, h >= 0);
             if (h >= 0) {
                 const int j = pos + __popc(m & ((1u << lane) - 1u));
+                LGN_ASSERT(j < total && slot0 + j < st->dbg_max_slots);
                 draw_h[slot0 + j] = h;
                 draw_s[slot0 + j] = (uint16_t)s;
             }
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_mark(const int32_t* __restrict
             for (int u = 0; u < U; u++) {
                 const int j = j0 + 32 * u + lane;
                 if (h[u] >= 0) {
+                    LGN_ASSERT(base + j < st->dbg_max_slots && (dd.bits == 0 || (uint32_t)h[u] < (1u << dd.bits)));
                     draw_v[base + j] = pv[u];
                     if (dd.bits) draw_key[base + j] = key[u];
                     wins += pv[u] == (CAND | (int32_t)(base + s[u])) ? 1 : 0;
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_assign(
                 int32_t src_off;
                 if (win[u]) {                       // Kernels.cu:418-438
                     const long long pos = (long long)hs.node_base + pn + rank[u];
+                    LGN_ASSERT(pos >= hs.node_base && pos <= st->dbg_capacity && key[u] >= 0);
                     if (pos < capacity) {
                         ids[pos] = key[u];
                         dedup_publish(dd, h[u], key[u], gen_base | (int32_t)pos, keep);
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_assign(
                     src_off = pv[u] < CAND ? pv[u] : -2 - h[u];   // winner of this hop numbered elsewhere: read it through the entry later
                 }
                 const long long e = e0 + j;
+                LGN_ASSERT(e >= hs.edge_base && e <= st->dbg_capacity && dst_off[u] >= 0 && (src_off >= 0 || -2 - src_off == h[u]));
                 if (e < capacity) {                    // Kernels.cu:423-424, 441-445
                     agg_src_ids[e] = key[u];
                     agg_dst_ids[e] = src[u];
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(256) k_batch_end(const int32_t* __restrict__ i
 #pragma unroll
         for (int k = 0; k < 4; k++) fix[k] = so[k] < 0 ? dedup_payload(dd, -2 - so[k], keep) : so[k];
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (so[k] < 0) agg_src_off[e + k] = fix[k];
+        for (int k = 0; k < 4; k++) if (so[k] < 0) { LGN_ASSERT(e + k < n_edges && fix[k] >= 0 && fix[k] < CAND); agg_src_off[e + k] = fix[k]; }
     }
     if (PRESC) {
         const int total = st->hop[n_hops].node_base;   // nc[9] for two hops

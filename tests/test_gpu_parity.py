@@ -560,3 +560,68 @@ def test_capacity_overflow_is_reported(small):
     with pytest.raises(L.LegionError):
         r.batch_from_host(np.zeros(1000, np.int32), None)
     r.close()
+
+
+def test_parity_suite_against_the_assert_build():
+    """compute-sanitizer is closed on the measurement pool: the sampling / gather parity cases are repeated against the
+    debug build of the library (-DLGN_DEBUG: a device assert in front of every indexed write, common.cuh).  A tripped
+    assert surfaces as a CUDA error and fails the inner run."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dbg = os.path.join(root, "legion-1_b200", "_build", "liblegion_b200_dbg.so")
+    if not os.path.exists(dbg):
+        pytest.skip("debug build missing (make -C legion-1_b200/csrc debug)")
+    if os.environ.get("LGN_LIBRARY"):
+        pytest.skip("already running against an explicit library")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                          "sampling_bit_exact or edge_cases or full_neighbourhood or epoch or presampling or gather_bit_exact or run_batch"],
+                         env=dict(os.environ, LGN_LIBRARY=dbg), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout
+
+
+def test_slot_status_and_attached_buffers(small):
+    """lgn_sync_pipe_status reports a slot's overflow (the server dies on it before IPCPost); lgn_attach_buffers makes the
+    kernels write the caller's buffers and rejects buffers that cannot even hold the seeds or are misaligned."""
+    import ctypes as C
+    import legion_b200 as L
+    from oracle import oracle as O
+    d = small
+    fanout, B = [5, 4], 64
+    ip, ix, ft = L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices), L.DevArray.from_numpy(d.features)
+    r = L.Runner(d.n_nodes, d.dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=9, max_feature_rows=10)   # feature buffer too small
+    r.bind_topology(ip, ix); r.bind_features(ft)
+    seeds = d.train_ids[:B]
+    r.batch_from_host(seeds, None, step=0)
+    r.run_batch(with_features=True)
+    assert L.lib().lgn_sync_pipe_status(r.handle, 0) == L._lib.E_CAPACITY
+    r.close()
+    r = L.Runner(d.n_nodes, d.dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=9)
+    r.bind_topology(ip, ix); r.bind_features(ft)
+    cap = r.capacity
+    mine = dict(ids=L.DevArray.zeros((cap,), np.int32), features=L.DevArray.zeros((cap, d.dim), np.float32), labels=L.DevArray.zeros((B,), np.int32),
+                agg_src=L.DevArray.zeros((cap,), np.int32), agg_dst=L.DevArray.zeros((cap,), np.int32),
+                node_counter=L.DevArray.zeros((16,), np.int32), edge_counter=L.DevArray.zeros((16,), np.int32))
+    v = L._lib.BatchView()
+    for k, a in mine.items():
+        setattr(v, k, a.ptr)
+    v.capacity, v.max_rows = cap, cap
+    L._lib.check(L.lib().lgn_attach_buffers(r.handle, 0, C.byref(v)), "lgn_attach_buffers")
+    r.batch_from_host(seeds, d.labels[seeds], step=0, pipe=0)
+    r.run_batch(with_features=True)
+    assert L.lib().lgn_sync_pipe_status(r.handle, 0) == 0
+    want = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=9).sample(seeds, step=0)
+    total, n_e = int(want["nc"][0]), int(want["ec"][0])
+    assert np.array_equal(mine["node_counter"].numpy(), want["nc"]) and np.array_equal(mine["edge_counter"].numpy(), want["ec"])
+    assert np.array_equal(mine["ids"].numpy(total), want["sampled_ids"][:total])
+    assert np.array_equal(mine["agg_src"].numpy(n_e), want["agg_src_off"][:n_e]) and np.array_equal(mine["agg_dst"].numpy(n_e), want["agg_dst_off"][:n_e])
+    assert np.array_equal(mine["features"].numpy(total).view(np.uint32), d.features[want["sampled_ids"][:total]].view(np.uint32))
+    assert np.array_equal(mine["labels"].numpy(), d.labels[seeds])
+    bad = L._lib.BatchView()
+    bad.ids, bad.capacity = mine["ids"].ptr, B - 1                       # cannot hold the seeds
+    assert L.lib().lgn_attach_buffers(r.handle, 1, C.byref(bad)) == L._lib.E_CAPACITY
+    bad = L._lib.BatchView()
+    bad.agg_src, bad.capacity = mine["agg_src"].ptr + 4, cap             # 128-bit accesses need 16-byte alignment
+    assert L.lib().lgn_attach_buffers(r.handle, 1, C.byref(bad)) == -1
+    r.close()
