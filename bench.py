@@ -447,7 +447,15 @@ def run_b200(args):
     train_steps = cluster.train_steps(my_train.numel(), B, dist if world > 1 else None)    # CUDA_IPC_Service.cu:88
 
     r = L.Runner(N, D, B, fanout, device=local, part=rank, rng_mode=rng_mode, rng_seed=42, enable_hotness=True, n_lanes=args.lanes)
-    r.bind_topology(ds.indptr, ds.indices)            # topology replicated in HBM (7 % of one B200 even for papers100M)
+    topo = (ds.indptr, ds.indices)
+    if os.environ.get("LGN_BENCH_TOPO_ALLOC") == "vmm":     # experiment: CSR in VMM allocations of 512 MB granules (address-translation reach)
+        topo = []
+        for t, dt in ((ds.indptr, np.int64), (ds.indices, np.int32)):
+            a, fd_, _mb = L.shared_alloc((t.numel(),), dt)
+            os.close(fd_)
+            L._lib.check(L.lib().lgn_copy_d2d(C.c_void_p(a.ptr), C.c_void_p(t.data_ptr()), C.c_int64(t.numel() * t.element_size())), "copy CSR")
+            topo.append(a)
+    r.bind_topology(topo[0], topo[1])            # topology replicated in HBM (7 % of one B200 even for papers100M)
     r.bind_seeds(L.MODE_TRAIN, my_train, my_labels)
     NL = args.lanes
     lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]     # one sampling stream per batch slot
@@ -488,11 +496,13 @@ def run_b200(args):
         else:                   # default: ncclAllReduce inside liblegion_b200.so (lgn_comm_*), torch only ships the unique id
             cluster.native_allreduce_u32(dist, nh.ptr, N, stream=sp)
         torch.cuda.synchronize()
-    order = L.hot_order(nh)
+    order, hot_sorted = L.hot_order(nh, want_sorted=True)
     kg = world
     n_cached = int(N * args.cache_frac)
     budget_gb = args.gpu_cache_gb if args.gpu_cache_gb > 0 else (38.0 if world > 1 else N * row_bytes / 1e9 + 1.0)
     budget_rows = int(budget_gb * 1e9 // row_bytes)
+
+    hbm_peak, peak_src = peaks()
 
     # ---- link probes for the hit-mix roofline (measured, not nominal) ----
     def copy_GBps(dst, src, nbytes, reps=4):
@@ -519,17 +529,21 @@ def run_b200(args):
     def build_cache(placement):
         c = Cache()
         c.placement = placement
-        if placement == "replicated" or kg == 1:
-            c.n_repl = min(n_cached, budget_rows) if placement == "replicated" else 0
-        elif placement == "hybrid":      # replicate as many of the hottest rows as the budget allows, partition the rest
-            c.n_repl = max(0, min(n_cached, (budget_rows * kg - n_cached) // (kg - 1)))
-        else:
-            c.n_repl = 0
         if placement == "replicated":
+            c.n_repl = min(n_cached, budget_rows)
             c.cap = max(1, c.n_repl)
-        else:
-            part_rows = min(n_cached - c.n_repl, max(0, budget_rows - c.n_repl) * kg)
-            c.cap = c.n_repl + cluster.capacity_for(part_rows, kg)
+        elif placement == "hybrid" and kg > 1:
+            # the B200 placement model (lgn_plan_hybrid): replicated / partitioned / host split that
+            # minimises the expected gather time of the presampled epoch under the three tier rates (payload GB/s per GPU:
+            # HBM copy / 2, the all-to-all random-row NVLink rate tools/peer_probe measured, the PCIe rate measured above)
+            c.n_repl, c.cap, _cost = L.plan_hybrid(hot_sorted, D, int(min(budget_gb * 1e9, n_cached * row_bytes + row_bytes)), kg,
+                                                   hbm_peak / 2, 640.0, pcie_h2d, stream=sp)
+            c.n_repl = min(c.n_repl, n_cached)                   # --cache-frac: rows beyond n_cached stay on the host tier
+            c.cap = min(c.cap, c.n_repl + cluster.capacity_for(n_cached - c.n_repl, kg)) if n_cached > c.n_repl else max(1, c.n_repl)
+        else:                            # reference partition (GPUCache.cu:103-108); one GPU: everything the budget allows, locally
+            c.n_repl = 0
+            part_rows = min(n_cached, budget_rows * kg)
+            c.cap = cluster.capacity_for(part_rows, kg)
         if kg > 1 and c.n_repl >= n_cached:      # nothing is partitioned: every GPU holds the whole cached set, no peer shards to bind
             c.kg_bind, part_bind = 1, 0
         else:
@@ -546,13 +560,15 @@ def run_b200(args):
                     host_tier[0].array[lo:lo + rows] = ds.features[lo:lo + rows].cpu().numpy()
             base = host_tier[0]
         r.bind_features(base)
-        c.vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm" and c.kg_bind > 1
+        c.vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm"      # shard through the VMM API (512 MB granules) instead of cudaMalloc
         shard_fd = mapped_bytes = None
         out = None
         if c.vmm:
             out, shard_fd, mapped_bytes = L.shared_alloc((c.cap, D), np.float32)
         c.my_shard = L.fill_feature_shard_hybrid(order, c.cap, c.kg_bind, part_bind, c.n_repl, ds.features, D, out=out)
         c.shards = [c.my_shard]
+        if c.kg_bind == 1 and c.vmm:
+            os.close(shard_fd)
         if c.kg_bind > 1 and c.vmm:
             torch.cuda.synchronize()
             fds = cluster.exchange_fds(dist, shard_fd)
@@ -720,7 +736,6 @@ def run_b200(args):
         return float(t.item()), prof
 
     K, W = args.steps, max(args.warmup, 3)
-    hbm_peak, peak_src = peaks()
 
     def count_work(K, W):
         """work done in the timed steps (deterministic: replay the same steps untimed and read the counters)."""
