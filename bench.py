@@ -539,6 +539,9 @@ def run_b200(args):
             c.n_repl, c.cap, _cost = L.plan_hybrid(hot_sorted, D, int(min(budget_gb * 1e9, n_cached * row_bytes + row_bytes)), kg,
                                                    hbm_peak / 2, 640.0, pcie_h2d, stream=sp)
             c.n_repl = min(c.n_repl, n_cached)                   # --cache-frac: rows beyond n_cached stay on the host tier
+            if budget_rows * kg >= n_cached:                     # the clique can hold every cacheable row: never spill to the host
+                c.n_repl = min(c.n_repl, max(0, (budget_rows * kg - n_cached) // (kg - 1)))     # tier for the sake of one more replica
+                c.cap = c.n_repl + cluster.capacity_for(n_cached - c.n_repl, kg)
             c.cap = min(c.cap, c.n_repl + cluster.capacity_for(n_cached - c.n_repl, kg)) if n_cached > c.n_repl else max(1, c.n_repl)
         else:                            # reference partition (GPUCache.cu:103-108); one GPU: everything the budget allows, locally
             c.n_repl = 0
@@ -554,6 +557,14 @@ def run_b200(args):
         cached_rows = c.n_repl + (c.cap - c.n_repl) * c.kg_bind
         if cached_rows < N:       # misses: pinned host memory over UVA (only then is the 4*N*D-byte host copy made)
             if host_tier[0] is None:
+                try:
+                    import psutil
+                    avail = psutil.virtual_memory().available
+                except Exception:      # noqa: BLE001
+                    avail = 1 << 62
+                if N * row_bytes * world > 0.6 * avail:      # every rank pins its own host copy of the feature matrix
+                    raise SystemExit(f"host tier needs {N * row_bytes * world / 1e9:.0f} GB of pinned host memory over {world} ranks, "
+                                     f"{avail / 1e9:.0f} GB available: raise --gpu-cache-gb / --cache-frac or lower --nodes")
                 host_tier[0] = L.MappedHostArray((N, D), np.float32)
                 rows = max(1, (1 << 28) // row_bytes)
                 for lo in range(0, N, rows):
@@ -627,9 +638,25 @@ def run_b200(args):
         (8 private copies of papers100M's 7.4 GB CSR would not fit every box)."""
         if world == 1:
             return ds.indptr.cpu().numpy(), ds.indices.cpu().numpy()
-        tok = [os.urandom(4).hex() if rank == 0 else None]
+        need = 8 * (N + 1) + 4 * ds.n_edges
+        where = None
+        if rank == 0:      # a tmpfs that is too small would kill the writer with SIGBUS: look before writing
+            import shutil
+            import tempfile
+            for cand in ("/dev/shm", tempfile.gettempdir()):
+                try:
+                    if shutil.disk_usage(cand).free > 1.1 * need:
+                        where = cand
+                        break
+                except OSError:
+                    pass
+        tok = [(os.urandom(4).hex(), where) if rank == 0 else None]
         dist.broadcast_object_list(tok, src=0)
-        paths = ["/dev/shm/lgn_bench_%s_%s" % (tok[0], nm) for nm in ("indptr", "indices")]
+        tok, where = tok[0]
+        if where is None:       # no shared place large enough: private copies
+            return ds.indptr.cpu().numpy(), ds.indices.cpu().numpy()
+        tok = [tok]
+        paths = ["%s/lgn_bench_%s_%s" % (where, tok[0], nm) for nm in ("indptr", "indices")]
         specs = [(ds.indptr, np.int64), (ds.indices, np.int32)]
         if rank == 0:
             for path, (t, dt) in zip(paths, specs):

@@ -260,11 +260,12 @@ int lgn_cost_model(const uint32_t* af_sorted_dev, const uint32_t* at_sorted_dev,
 /* B200 placement model (no reference counterpart): how many of the hottest feature rows to replicate on
  * every GPU of the clique before the rest is partitioned and what stays on the host, given the per-GPU byte budget for
  * features and the three tier bandwidths (any common unit).  af_sorted_dev = presampled hotness in hot order (the
- * sorted counts of lgn_hot_order).  Outputs feed lgn_place_hybrid / lgn_fill_feature_shard_hybrid: *n_repl rows are
+ * sorted counts of lgn_hot_order); `prior` = pseudo-count added to every row (rows one presampling epoch never saw
+ * are still read now and then: with prior > 0 they are kept off the host tier while the clique has room).  Outputs feed lgn_place_hybrid / lgn_fill_feature_shard_hybrid: *n_repl rows are
  * replicated, *cap is the shard height. */
 int lgn_plan_hybrid(const uint32_t* af_sorted_dev, int64_t n, int32_t dim, int64_t budget_bytes, int32_t kg,
-                    double bw_local, double bw_peer, double bw_host, int64_t* n_repl, int64_t* cap, double* est_cost,
-                    void* stream);
+                    double bw_local, double bw_peer, double bw_host, double prior, int64_t* n_repl, int64_t* cap,
+                    double* est_cost, void* stream);
 
 /* ------------------------------------------------------------------ collective
  * The path's one collective: the sum of the per-GPU hotness histograms before planning.  Replaces the leader's P2P

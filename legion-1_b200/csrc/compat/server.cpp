@@ -511,7 +511,7 @@ public:
                 int64_t cap64 = 0;
                 double cost = 0;
                 const double bw_local = 3272.0, bw_peer = 640.0, bw_host = 50.0;     // GB/s payload per GPU: HBM copy / 2, measured NVLink gather, PCIe Gen5 zero-copy
-                LGN_DIE(lgn_plan_hybrid((uint32_t*)af, N, ds_.dim, feat_budget, kg, bw_local, bw_peer, bw_host, &n_repl, &cap64, &cost, nullptr), "lgn_plan_hybrid");
+                LGN_DIE(lgn_plan_hybrid((uint32_t*)af, N, ds_.dim, feat_budget, kg, bw_local, bw_peer, bw_host, /*prior=*/0.5, &n_repl, &cap64, &cost, nullptr), "lgn_plan_hybrid");
                 ncap = (int32_t)cap64;
                 if (topo_replicated) ecap = 0;
                 std::cout << "Placement: hybrid, " << n_repl << " hottest rows replicated, " << (cap64 - n_repl) * kg << " partitioned over " << kg

@@ -283,13 +283,13 @@ extern "C" int lgn_cost_model(const uint32_t* af, const uint32_t* at, const int3
 // what stays on the host.  For n_repl replicated rows the per-GPU budget leaves room for (budget/row - n_repl) * kg
 // partitioned rows; the expected time of one epoch's gathers is
 //     t = H(n_repl)/bw_local + [H(n_repl + n_part) - H(n_repl)] * (1/kg/bw_local + (kg-1)/kg/bw_peer) + [H(N) - H(n_repl + n_part)]/bw_host
-// with H the cumulative presampled hotness in hot order.  101 candidate splits are evaluated, the cheapest wins.
+// with H(k) = presampled hotness of the k hottest rows + prior * k (a pseudo-count per row).  101 candidate splits are evaluated, the cheapest wins.
 extern "C" int lgn_plan_hybrid(const uint32_t* af_sorted, int64_t n, int32_t dim, int64_t budget_bytes, int32_t kg,
-                               double bw_local, double bw_peer, double bw_host, int64_t* n_repl_out, int64_t* cap_out,
-                               double* est_cost, void* stream)
+                               double bw_local, double bw_peer, double bw_host, double prior, int64_t* n_repl_out,
+                               int64_t* cap_out, double* est_cost, void* stream)
 {
     if (!af_sorted || n <= 0 || dim <= 0 || budget_bytes <= 0 || kg <= 0 || kg > LGN_MAX_PARTS || !n_repl_out || !cap_out) return LGN_E_ARG;
-    if (!(bw_local > 0) || !(bw_peer > 0) || !(bw_host > 0)) return LGN_E_ARG;
+    if (!(bw_local > 0) || !(bw_peer > 0) || !(bw_host > 0) || !(prior >= 0)) return LGN_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t row = (int64_t)dim * 4;
     const int64_t budget_rows = budget_bytes / row;
@@ -329,7 +329,12 @@ extern "C" int lgn_plan_hybrid(const uint32_t* af_sorted, int64_t n, int32_t dim
     int best = 0;
     double best_t = -1.0;
     for (int i = 0; i < n_pts; i++) {
-        const double t = (double)h_repl[i] / bw_local + (double)(h_all[i] - h_repl[i]) * c_mix + (double)(total - h_all[i]) / bw_host;
+        // H(k) + prior * k: a row presampling never saw still gets `prior` expected reads per epoch, so rows are not pushed
+        // to the host tier (12x the cost of a peer read) merely because ONE epoch of samples missed them
+        const double hr = (double)h_repl[i] + prior * (double)repl[i];
+        const double ha = (double)h_all[i] + prior * (double)(repl[i] + part[i]);
+        const double ht = (double)total + prior * (double)n;
+        const double t = hr / bw_local + (ha - hr) * c_mix + (ht - ha) / bw_host;
         if (best_t < 0 || t < best_t) { best_t = t; best = i; }
         if (kg == 1) break;
     }

@@ -311,12 +311,12 @@ def cost_model(af_sorted, at_sorted, qt, indptr, dim, cache_memory, kg, topo_tra
     return ncap.value, ecap.value
 
 
-def plan_hybrid(af_sorted, dim, budget_bytes, kg, bw_local, bw_peer, bw_host, stream=None):
+def plan_hybrid(af_sorted, dim, budget_bytes, kg, bw_local, bw_peer, bw_host, prior=0.5, stream=None):
     """B200 placement model (lgn_plan_hybrid): -> (n_repl, cap, estimated cost)."""
     n = af_sorted.shape[0]
     n_repl, cap, cost = C.c_int64(), C.c_int64(), C.c_double()
     check(lib().lgn_plan_hybrid(_ptr(af_sorted), C.c_int64(n), C.c_int32(dim), C.c_int64(int(budget_bytes)), C.c_int32(kg),
-                                C.c_double(bw_local), C.c_double(bw_peer), C.c_double(bw_host), C.byref(n_repl), C.byref(cap),
+                                C.c_double(bw_local), C.c_double(bw_peer), C.c_double(bw_host), C.c_double(prior), C.byref(n_repl), C.byref(cap),
                                 C.byref(cost), _vp(stream)), "lgn_plan_hybrid")
     return n_repl.value, cap.value, cost.value
 

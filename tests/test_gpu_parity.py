@@ -279,8 +279,9 @@ def test_plan_hybrid_picks_the_cheapest_split(kg, budget_frac):
     row = dim * 4
     budget = int(n * row * budget_frac)
     bw_l, bw_p, bw_h = 3272.0, 640.0, 50.0
-    n_repl, cap, cost = L.plan_hybrid(L.DevArray.from_numpy(counts), dim, budget, kg, bw_l, bw_p, bw_h)
-    H = np.concatenate([[0], np.cumsum(counts.astype(np.uint64))]).astype(np.float64)
+    prior = 0.5 if kg == 8 else 0.0
+    n_repl, cap, cost = L.plan_hybrid(L.DevArray.from_numpy(counts), dim, budget, kg, bw_l, bw_p, bw_h, prior=prior)
+    H = np.concatenate([[0], np.cumsum(counts.astype(np.uint64))]).astype(np.float64) + prior * np.arange(n + 1)
     budget_rows = budget // row
     best = None
     for i in range(101):
