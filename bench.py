@@ -69,6 +69,9 @@ def parse():
                     help="feature cache over the N GPUs: reference round-robin partition | hot rows replicated + rest partitioned | all replicated")
     ap.add_argument("--gpu-cache-gb", type=float, default=0.0,
                     help="per-GPU feature-cache budget; 0 = the launcher's 38 GB when N > 1 (legion_server.py), the whole table when N = 1")
+    ap.add_argument("--topology", default="replicated", choices=["replicated", "sharded"],
+                    help="CSR: a full copy in every GPU's HBM (default; 7 %% of a B200 for papers100M) | the reference's partition by topology hotness "
+                         "over the clique (GPU_Memory_Graph_Storage.cu:14-133), sampled through NVLink P2P loads")
     ap.add_argument("--no-extra-sharded", action="store_true", help="skip the second measurement with the reference partition (N > 1)")
     ap.add_argument("--no-train-epoch", action="store_true", help="skip the GraphSAGE epoch-time leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing oracle check (debug)")
@@ -498,6 +501,38 @@ def run_b200(args):
         torch.cuda.synchronize()
     order, hot_sorted = L.hot_order(nh, want_sorted=True)
     kg = world
+    topo_note = "topology replicated in HBM"
+    topo_keep = []
+    if args.topology == "sharded" and world > 1:
+        # the reference's topology cache: nodes in topology-hotness order dealt round-robin over the clique, GPU j holds the
+        # adjacency lists of ranks j, j + Kg, ..; the sampler resolves a frontier node through slot_of and reads the indptr
+        # pair and the neighbour ids from the owner's shard (local HBM or NVLink)
+        cluster.native_allreduce_u32(dist, _th.ptr, N, stream=sp)
+        torch.cuda.synchronize()
+        order_t = L.hot_order(_th)
+        cap_t = cluster.capacity_for(N, kg)
+        ip_s, ix_s, n_ix = L.fill_topo_shard(order_t, cap_t, kg, rank, ds.indptr, ds.indices)
+        torch.cuda.synchronize()
+        tabs = []
+        for arr, shape, dt in ((ip_s, (cap_t + 1,), np.int64), (ix_s, None, np.int32)):
+            h = (C.c_uint8 * 64)()
+            L._lib.check(L.lib().lgn_ipc_export(C.c_void_p(arr.ptr), h), "ipc_export")
+            meta = [None] * world
+            dist.all_gather_object(meta, (bytes(h), int(arr.shape[0])))
+            lst = []
+            for j in range(world):
+                if j == rank:
+                    lst.append(arr)
+                    continue
+                pp = C.c_void_p()
+                hb = (C.c_uint8 * 64).from_buffer_copy(meta[j][0])
+                L._lib.check(L.lib().lgn_ipc_import(hb, C.byref(pp)), "ipc_import")
+                lst.append(L.DevArray((meta[j][1],), dt, ptr=pp.value, owner=False))
+            tabs.append(lst)
+        slot_t = L.place(order_t, cap_t, kg)
+        r.bind_topology_cache(tabs[0], tabs[1], slot_t, cap_t)
+        topo_keep = [ip_s, ix_s, slot_t, tabs]
+        topo_note = f"topology partitioned over {kg} GPUs by topology hotness ({n_ix} neighbour ids in this GPU's shard), sampled over NVLink"
     n_cached = int(N * args.cache_frac)
     budget_gb = args.gpu_cache_gb if args.gpu_cache_gb > 0 else (38.0 if world > 1 else N * row_bytes / 1e9 + 1.0)
     budget_rows = int(budget_gb * 1e9 // row_bytes)
@@ -923,7 +958,7 @@ def run_b200(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 ids / f32 rows (bit copy)", "data": "synthetic",
             "config": {"workload": workload_string(args, cfg, ds.n_edges),
-                       "parallelism": f"dp{world}: seeds tid%{world}, feature cache {c.placement} over {kg} GPU(s), topology replicated in HBM",
+                       "parallelism": f"dp{world}: seeds tid%{world}, feature cache {c.placement} over {kg} GPU(s), {topo_note}",
                        "placement": c.placement, "rows_replicated": int(c.n_repl), "rows_per_shard": int(c.cap), "cache_frac": args.cache_frac,
                        "gpu_cache_budget_GB": budget_gb, "batches_in_flight": NL,
                        "l2": "inputs larger than L2: working set (feature shard %.2f GB + %.2f GB CSR) against 126 MB; "
