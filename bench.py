@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nodes", type=int, default=0, help="override node count (debug)")
+    ap.add_argument("--batch", type=int, default=0, help="override the seeds per mini-batch (debug: fixed per-launch cost vs work)")
     ap.add_argument("--placement", default="hybrid", choices=["sharded", "hybrid", "replicated"],
                     help="feature cache over the N GPUs: reference round-robin partition | hot rows replicated + rest partitioned | all replicated")
     ap.add_argument("--gpu-cache-gb", type=float, default=0.0,
@@ -72,6 +73,9 @@ def parse():
     ap.add_argument("--topology", default="replicated", choices=["replicated", "sharded"],
                     help="CSR: a full copy in every GPU's HBM (default; 7 %% of a B200 for papers100M) | the reference's partition by topology hotness "
                          "over the clique (GPU_Memory_Graph_Storage.cu:14-133), sampled through NVLink P2P loads")
+    ap.add_argument("--slot-map", default="compact", choices=["compact", "int32"],
+                    help="row lookup of the feature cache: compact L2-resident placement map, rows of a class in node-id order "
+                         "(lgn_place_compact; a fully resident table is addressed directly) | int32 slot_of[N] in hotness order (the reference's arrangement)")
     ap.add_argument("--no-extra-sharded", action="store_true", help="skip the second measurement with the reference partition (N > 1)")
     ap.add_argument("--no-train-epoch", action="store_true", help="skip the GraphSAGE epoch-time leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing oracle check (debug)")
@@ -153,6 +157,8 @@ def workload(args):
     cfg = dict(L.synth.CONFIGS[args.config])
     if args.nodes:
         cfg["n_nodes"] = args.nodes
+    if args.batch:
+        cfg["batch"] = args.batch
     return cfg
 
 
@@ -587,9 +593,16 @@ def run_b200(args):
         else:
             c.kg_bind, part_bind = kg, rank
         r.set_part(part_bind)
-        c.slot_of = L.place_hybrid(order, c.cap, c.kg_bind, c.n_repl, part_bind)
+        cached_rows = min(N, c.n_repl + (c.cap - c.n_repl) * c.kg_bind)
+        c.compact = args.slot_map == "compact"
+        c.identity = c.compact and c.kg_bind == 1 and cached_rows >= N       # whole table resident: rows addressed by node id
+        if c.identity:
+            c.slot_of = None
+        elif c.compact:
+            c.slot_of = L.place_compact(order, min(c.n_repl, N), cached_rows - min(c.n_repl, N), stream=sp)
+        else:
+            c.slot_of = L.place_hybrid(order, c.cap, c.kg_bind, c.n_repl, part_bind)
         base = ds.features
-        cached_rows = c.n_repl + (c.cap - c.n_repl) * c.kg_bind
         if cached_rows < N:       # misses: pinned host memory over UVA (only then is the 4*N*D-byte host copy made)
             if host_tier[0] is None:
                 try:
@@ -606,12 +619,22 @@ def run_b200(args):
                     host_tier[0].array[lo:lo + rows] = ds.features[lo:lo + rows].cpu().numpy()
             base = host_tier[0]
         r.bind_features(base)
+        if c.identity:
+            c.my_shard = None
+            c.shards = [ds.features]
+            c.cap = c.n_repl = N
+            r.bind_feature_cache_compact(c.shards, None, N, N)
+            barrier()
+            return c
         c.vmm = os.environ.get("LGN_BENCH_SHARD_ALLOC", "ipc") == "vmm"      # shard through the VMM API (512 MB granules) instead of cudaMalloc
         shard_fd = mapped_bytes = None
         out = None
         if c.vmm:
             out, shard_fd, mapped_bytes = L.shared_alloc((c.cap, D), np.float32)
-        c.my_shard = L.fill_feature_shard_hybrid(order, c.cap, c.kg_bind, part_bind, c.n_repl, ds.features, D, out=out)
+        if c.compact:
+            c.my_shard = L.fill_feature_shard_compact(c.slot_of, N, c.n_repl, c.kg_bind, part_bind, ds.features, D, c.cap, out=out)
+        else:
+            c.my_shard = L.fill_feature_shard_hybrid(order, c.cap, c.kg_bind, part_bind, c.n_repl, ds.features, D, out=out)
         c.shards = [c.my_shard]
         if c.kg_bind == 1 and c.vmm:
             os.close(shard_fd)
@@ -645,7 +668,10 @@ def run_b200(args):
                 L._lib.check(L.lib().lgn_ipc_import(hb, C.byref(p)), "ipc_import")
                 c.imported.append(p)
                 c.shards.append(L.DevArray((c.cap, D), np.float32, ptr=p.value, owner=False))
-        r.bind_feature_cache(c.shards, c.slot_of, c.cap)
+        if c.compact:
+            r.bind_feature_cache_compact(c.shards, c.slot_of, c.n_repl, c.cap)
+        else:
+            r.bind_feature_cache(c.shards, c.slot_of, c.cap)
         barrier()
         return c
 
@@ -657,11 +683,13 @@ def run_b200(args):
             else:
                 L.lib().lgn_ipc_close(p)
         barrier()                      # every importer has unmapped before any owner frees
-        if c.vmm:
-            L.shared_free(c.my_shard)
-        else:
-            c.my_shard.free()
-        c.slot_of.free()
+        if c.my_shard is not None:
+            if c.vmm:
+                L.shared_free(c.my_shard)
+            else:
+                c.my_shard.free()
+        if c.slot_of is not None:
+            c.slot_of.free()
         c.shards, c.imported = [], []
 
     # ---- parity: one mini-batch of THIS rank against the CPU oracle, through the real tier mappings ----
@@ -855,6 +883,7 @@ def run_b200(args):
             dist.all_reduce(tot)
         nvl = nvlink_probe(c) or 770.0
         return {"placement": c.placement, "rows_replicated": int(c.n_repl), "rows_per_shard": int(c.cap),
+                "slot_map": "none" if c.identity else "compact" if c.compact else "int32",
                 "value": float(tot[0].item()) / (ms_total / 1e3), "unit": UNIT, "ms_per_step": ms_total / K,
                 "feature_extract_GBps": float(tot[1].item()) * row_bytes / (ms_total / 1e3) / 1e9,
                 "tier_rows_per_timed_region": [int(t * K / (K + W)) for t in tiers],
@@ -960,6 +989,8 @@ def run_b200(args):
             "config": {"workload": workload_string(args, cfg, ds.n_edges),
                        "parallelism": f"dp{world}: seeds tid%{world}, feature cache {c.placement} over {kg} GPU(s), {topo_note}",
                        "placement": c.placement, "rows_replicated": int(c.n_repl), "rows_per_shard": int(c.cap), "cache_frac": args.cache_frac,
+                       "slot_map": ("none: whole table resident in node-id order, rows addressed directly" if c.identity else
+                                    "compact L2-resident placement map (lgn_place_compact)" if c.compact else "int32 slot_of[N], hotness order"),
                        "gpu_cache_budget_GB": budget_gb, "batches_in_flight": NL,
                        "l2": "inputs larger than L2: working set (feature shard %.2f GB + %.2f GB CSR) against 126 MB; "
                              "consecutive steps touch different rows" % (c.cap * row_bytes / 1e9, (8 * N + 4 * ds.n_edges) / 1e9),
@@ -1099,7 +1130,8 @@ def probe_mode(L, r, dist, world, rank, c, lp, lanes, stream, sp, NL, B, D, trai
         for i in range(n):
             step_resident(i)
     both(8)
-    log(f"rank {rank} full pipeline, {NL} lanes: {ev_time(both, 40):.4f} ms/step")
+    both(64)
+    log(f"rank {rank} full pipeline, {NL} lanes: {ev_time(both, 400):.4f} ms/step")
     if os.environ.get("LGN_NCU_RANGE"):       # ncu --replay-mode app-range: whole-range metrics under real concurrency
         def samp4(n):
             for i in range(n):

@@ -139,6 +139,11 @@ int lgn_bind_features(lgn_ctx* ctx, const float* features_dev);
  * cuckoo map, GPUCache.cu:387-432); shard_tab = Global_Float_Feature_Cache. */
 int lgn_bind_feature_cache(lgn_ctx* ctx, int32_t n_parts, const float* const* shard_tab,
                            const int32_t* slot_of_dev, int64_t cap);
+/* the same with a compact placement map (lgn_place_compact).  cmap_dev = NULL with n_repl = n_nodes binds
+ * shard_tab[part of this GPU] as the WHOLE feature matrix resident in node-id order: rows are addressed directly,
+ * no lookup. */
+int lgn_bind_feature_cache_compact(lgn_ctx* ctx, int32_t n_parts, const float* const* shard_tab, const void* cmap_dev,
+                                   int64_t n_repl, int64_t cap);
 
 /* ------------------------------------------------------------------ hot path
  * One call per reference operator (Operator.cu:10-123); all asynchronous. */
@@ -247,6 +252,22 @@ int lgn_place_hybrid(const int32_t* order_dev, int64_t n, int64_t cap, int32_t k
                      int32_t* slot_of_dev, void* stream);
 int lgn_fill_feature_shard_hybrid(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j, int64_t n_repl,
                                   const float* features_dev, int32_t dim, float* shard_dev, void* stream);
+/* B200 extension: COMPACT placement map.  Same three classes as the hybrid placement (the n_repl hottest ranks of
+ * `order` replicated on every GPU, the next n_part ranks partitioned over kg GPUs, the rest on the host tier), but the
+ * rows of a class are stored in NODE-ID order, so the map needs no row number: one 32-byte record per LGN_CMAP_NODES
+ * nodes { u32 replicated nodes before the record, u32 partitioned nodes before it, 3 x u32 "replicated" bits,
+ * 3 x u32 "partitioned" bits }.  A replicated node's row is its rank among replicated nodes (prefix + popcount);
+ * a partitioned node with rank q among partitioned nodes lives on GPU q % kg, row n_repl + q / kg.  The map of
+ * papers100M is 37 MB and stays in L2, where int32 slot_of[N] (444 MB) costs a random DRAM access per gathered row.
+ * Replaces FindFeat's cuckoo probe (GPUCache.cu:387-432) like lgn_place; which rows are cached where is still
+ * decided by hotness rank (GPUCache.cu:103-108), only the order inside a shard differs.  The map is the same on
+ * every GPU of the clique. */
+#define LGN_CMAP_NODES 96
+int64_t lgn_cmap_bytes(int64_t n_nodes);
+int lgn_place_compact(const int32_t* order_dev, int64_t n, int64_t n_repl, int64_t n_part, void* cmap_dev, void* stream);
+/* shard j (height cap >= n_repl + ceil(n_part / kg)) of that placement: a streaming pass over the feature matrix */
+int lgn_fill_feature_shard_compact(const void* cmap_dev, int64_t n, int64_t n_repl, int32_t kg, int32_t j,
+                                   const float* features_dev, int32_t dim, float* shard_dev, int64_t cap, void* stream);
 /* topology shard j (GraphCache, GPU_Memory_Graph_Storage.cu:98-133). Pass
  * indices_out_dev = NULL to size it: *n_indices receives the count (host sync). */
 int lgn_fill_topo_shard(const int32_t* order_dev, int64_t n, int64_t cap, int32_t kg, int32_t j,

@@ -6,4 +6,4 @@ from . import _lib, synth  # noqa: F401
 from ._lib import (DevArray, MappedHostArray, LegionError, RNG_MINSTD, RNG_PHILOX,  # noqa: F401
                    MODE_TRAIN, MODE_VALID, MODE_TEST, build, lib)
 from .runner import (Runner, hot_order, place, fill_feature_shard, fill_topo_shard, cost_model,  # noqa: F401
-                     coordinate, place_hybrid, fill_feature_shard_hybrid, plan_hybrid, Stream, shared_alloc, shared_import, shared_free)
+                     coordinate, place_hybrid, fill_feature_shard_hybrid, plan_hybrid, place_compact, fill_feature_shard_compact, Stream, shared_alloc, shared_import, shared_free)

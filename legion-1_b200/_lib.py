@@ -71,6 +71,7 @@ def lib():
         L.lgn_error_string.restype = C.c_char_p
         L.lgn_last_cuda_error.restype = C.c_char_p
         L.lgn_capacity.restype = C.c_int64
+        L.lgn_cmap_bytes.restype = C.c_int64
         L.lgn_max_ids.restype = C.c_int32
         L.lgn_mode_of_step.restype = C.c_int32
         L.lgn_local_batch_id.restype = C.c_int32

@@ -532,6 +532,7 @@ public:
             std::vector<const int64_t*> tptr(kg);
             std::vector<const int32_t*> tidx(kg);
             std::vector<int32_t*> fslot(kg), tslot(kg);
+            std::vector<void*> fcmap(kg, nullptr);
             for (int j = 0; j < kg; j++) {
                 const int dev = lead + j;
                 LGN_DIE(lgn_set_device(dev), "set device");
@@ -540,11 +541,22 @@ public:
                     LGN_DIE(lgn_device_alloc(&oq, N * 4), "alloc"); LGN_DIE(lgn_device_alloc(&ot, N * 4), "alloc");
                     LGN_DIE(lgn_copy_d2d(oq, qf, N * 4), "copy order"); LGN_DIE(lgn_copy_d2d(ot, qt, N * 4), "copy order");
                 }
-                void *shard = nullptr, *fs = nullptr, *ts = nullptr, *tip = nullptr, *tix = nullptr;
+                void *shard = nullptr, *fs = nullptr, *ts = nullptr, *tip = nullptr, *tix = nullptr, *cm = nullptr;
                 LGN_DIE(lgn_device_alloc(&shard, (int64_t)ncap * ds_.dim * 4), "alloc feature shard");
-                LGN_DIE(lgn_device_alloc(&fs, N * 4), "alloc"); LGN_DIE(lgn_device_alloc(&ts, N * 4), "alloc");
-                LGN_DIE(lgn_fill_feature_shard_hybrid((int32_t*)oq, N, ncap, kg, j, n_repl, ds_.feat_d, ds_.dim, (float*)shard, nullptr), "FeatFillUp");
-                LGN_DIE(lgn_place_hybrid((int32_t*)oq, N, ncap, kg, n_repl, j, (int32_t*)fs, nullptr), "InitPair");
+                if (!hybrid) LGN_DIE(lgn_device_alloc(&fs, N * 4), "alloc");
+                LGN_DIE(lgn_device_alloc(&ts, N * 4), "alloc");
+                if (hybrid) {
+                    // compact placement map (37 MB for papers100M: L2-resident) instead of int32 slot_of[N]; rows of a class in
+                    // node-id order, so FeatFillUp is one streaming pass over the feature matrix
+                    int64_t n_part = ((int64_t)ncap - n_repl) * kg;
+                    if (n_part > N - n_repl) n_part = N - n_repl;
+                    LGN_DIE(lgn_device_alloc(&cm, lgn_cmap_bytes(N)), "alloc placement map");
+                    LGN_DIE(lgn_place_compact((int32_t*)oq, N, n_repl, n_part, cm, nullptr), "InitPair (compact)");
+                    LGN_DIE(lgn_fill_feature_shard_compact(cm, N, n_repl, kg, j, ds_.feat_d, ds_.dim, (float*)shard, ncap, nullptr), "FeatFillUp");
+                } else {
+                    LGN_DIE(lgn_fill_feature_shard_hybrid((int32_t*)oq, N, ncap, kg, j, n_repl, ds_.feat_d, ds_.dim, (float*)shard, nullptr), "FeatFillUp");
+                    LGN_DIE(lgn_place_hybrid((int32_t*)oq, N, ncap, kg, n_repl, j, (int32_t*)fs, nullptr), "InitPair");
+                }
                 if (topo_replicated) {      // full CSR copy in this GPU's HBM: the sampler never leaves the device
                     LGN_DIE(lgn_device_alloc(&tip, (int64_t)(N + 1) * 8), "alloc");
                     LGN_DIE(lgn_device_alloc(&tix, (ds_.n_edges > 0 ? ds_.n_edges : 1) * 4), "alloc");
@@ -560,12 +572,16 @@ public:
                 }
                 LGN_DIE(lgn_device_synchronize(), "sync");
                 fshard[j] = (float*)shard; fslot[j] = (int32_t*)fs; tslot[j] = (int32_t*)ts; tptr[j] = (int64_t*)tip; tidx[j] = (int32_t*)tix;
-                for (void* q : {shard, fs, ts, tip, tix}) owned_.push_back({dev, q});
+                fcmap[j] = cm;
+                for (void* q : {shard, fs, ts, tip, tix, cm}) if (q) owned_.push_back({dev, q});
                 if (j > 0) { lgn_device_free(oq); lgn_device_free(ot); }
             }
             for (int j = 0; j < kg; j++) {   // every GPU of the clique sees all shards (P2P) and its own replica of the maps
                 LGN_DIE(lgn_set_part(ctx_[lead + j], j), "lgn_set_part");
-                LGN_DIE(lgn_bind_feature_cache(ctx_[lead + j], kg, fshard.data(), fslot[j], ncap), "bind feature cache");
+                const bool resident = hybrid && (n_repl >= N || (kg == 1 && (int64_t)ncap >= N));   // whole matrix in this GPU's shard, id order
+                if (resident) LGN_DIE(lgn_bind_feature_cache_compact(ctx_[lead + j], kg, fshard.data(), nullptr, N, ncap), "bind resident features");
+                else if (hybrid) LGN_DIE(lgn_bind_feature_cache_compact(ctx_[lead + j], kg, fshard.data(), fcmap[j], n_repl, ncap), "bind feature cache (compact)");
+                else LGN_DIE(lgn_bind_feature_cache(ctx_[lead + j], kg, fshard.data(), fslot[j], ncap), "bind feature cache");
                 if (topo_replicated) LGN_DIE(lgn_bind_topology(ctx_[lead + j], tptr[j], tidx[j]), "bind topology (HBM copy)");
                 else LGN_DIE(lgn_bind_topology_cache(ctx_[lead + j], kg, tptr.data(), tidx.data(), tslot[j], ecap), "bind topology cache");
             }

@@ -94,6 +94,7 @@ int lgn_stream_create(void** stream, int32_t high_priority)
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     cudaStream_t s;
+    if (const char* lp = getenv("LGN_LANE_PRIO")) high_priority = lp[0] == 'h';     // experiment knob
     CK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
     *stream = (void*)s;
     return LGN_OK;
@@ -257,7 +258,9 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
             if (rc) return rc;
         }
         // gathers run at the lowest priority so the latency-bound sampling kernels get SM slots first
-        CK(cudaStreamCreateWithPriority(&pp.gather_stream, cudaStreamNonBlocking, prio_lo));
+        // (LGN_GATHER_PRIO=hi: experiment knob)
+        const char* gp = getenv("LGN_GATHER_PRIO");
+        CK(cudaStreamCreateWithPriority(&pp.gather_stream, cudaStreamNonBlocking, gp && gp[0] == 'h' ? prio_hi : prio_lo));
         for (int i = 0; i < LGN_MAX_HOPS + 2; i++) CK(cudaEventCreateWithFlags(&pp.ev_hop[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.ev_end, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pp.ev_done, cudaEventDisableTiming));
@@ -277,6 +280,7 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         if (c->gather_ctas_per_sm < 1) c->gather_ctas_per_sm = 1;
         auto knob = [](const char* name, int dflt) { const char* v = getenv(name); int x = v ? atoi(v) : dflt; return x < 1 ? 1 : x; };
         c->gather_ldg_ctas = getenv("LGN_GATHER_LDG_CTAS") ? knob("LGN_GATHER_LDG_CTAS", 8) : 0;   // 0 = auto
+        c->gather_unroll = knob("LGN_GATHER_UNROLL", 4);
         c->gather_threads = knob("LGN_GATHER_THREADS", 256);
         if (c->gather_threads > 256) c->gather_threads = 256;
         c->gather_threads = (c->gather_threads + 31) / 32 * 32;
@@ -412,10 +416,25 @@ int lgn_bind_feature_cache(lgn_ctx* c, int32_t n_parts, const float* const* shar
 {
     if (!c || n_parts < 0 || n_parts > LGN_MAX_PARTS) return LGN_E_ARG;
     invalidate_graphs(c);
+    c->feat.cmap = nullptr; c->feat.identity = 0;
     if (!slot_of || n_parts == 0) { c->feat.slot_of = nullptr; c->feat.n_parts = 0; return LGN_OK; }
     if (cap <= 0 || !shard_tab) return LGN_E_ARG;
     for (int i = 0; i < n_parts; i++) c->feat.shard_tab[i] = shard_tab[i];
     c->feat.cap = cap; c->feat.slot_of = slot_of; c->feat.n_parts = n_parts;
+    return LGN_OK;
+}
+int lgn_bind_feature_cache_compact(lgn_ctx* c, int32_t n_parts, const float* const* shard_tab, const void* cmap, int64_t n_repl, int64_t cap)
+{
+    if (!c || n_parts <= 0 || n_parts > LGN_MAX_PARTS || !shard_tab || n_repl < 0 || cap <= 0 || n_repl > cap) return LGN_E_ARG;
+    if (c->feat.my_part >= n_parts) return LGN_E_ARG;
+    if (!cmap && !(n_repl == c->cfg.n_nodes && cap >= n_repl)) return LGN_E_ARG;   // direct addressing needs the whole table in shard_tab[my_part]
+    if (cmap && ((uintptr_t)cmap & 15)) return LGN_E_ARG;
+    invalidate_graphs(c);
+    for (int i = 0; i < n_parts; i++) { if (!shard_tab[i]) return LGN_E_ARG; c->feat.shard_tab[i] = shard_tab[i]; }
+    c->feat.slot_of = nullptr;
+    c->feat.cmap = (const uint4*)cmap;
+    c->feat.identity = cmap ? 0 : 1;
+    c->feat.n_repl = n_repl; c->feat.kg = n_parts; c->feat.cap = cap; c->feat.n_parts = n_parts;
     return LGN_OK;
 }
 

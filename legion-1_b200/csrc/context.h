@@ -25,6 +25,12 @@ struct FeatView {
     long long cap;
     int32_t my_part;
     int32_t n_parts;
+    // compact placement (lgn_place_compact): one 32-byte record per 96 nodes, L2-resident for any N; rows of a class sit in
+    // node-id order, so a row index is a prefix count + a popcount (gather.cu: resolve_row)
+    const uint4* cmap;                          // NULL: slot_of (or nothing) is bound
+    long long n_repl;                           // rows [0, n_repl) of every shard hold the replicated class
+    int32_t kg;                                 // GPUs the partitioned class is dealt over
+    int32_t identity;                           // 1: every node is resident in shard_tab[my_part] at row = node id (no lookup at all)
 };
 
 // One pipeline slot = one independent lane: its own output buffers (the 7 IPC buffers of
@@ -96,6 +102,7 @@ struct lgn_ctx {
     int gather_mode;           // 0 = 128-bit LDG/STG warp-per-row, 1 = cp.async.bulk (TMA) thread-per-row, -1 = auto
     int gather_ctas_per_sm;
     int gather_ldg_ctas;       // CTAs per SM of the LDG gather
+    int gather_unroll;         // rows in flight per warp of the LDG gather (4, or 2: fewer registers)
     int gather_threads;        // rows in flight per CTA of the bulk-copy gather (<= 256)
     int shared_gather_stream;  // 1: all slots' gathers run back to back on one stream (one saturates HBM already)
     int sample_ctas_per_sm, resolve_ctas_per_sm, end_ctas_per_sm;   // grid caps (CTAs per SM) of the persistent kernels
@@ -116,6 +123,7 @@ void launch_batch_begin(lgn_ctx* c, cudaStream_t s, const int32_t* ids, const in
 void launch_sample_hop(lgn_ctx* c, cudaStream_t s, int hop, bool presc);
 void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc);
 int sample_items_per_tile();
+void sampler_set_carveout(int pct);
 // context.cu
 void reset_dedup(lgn_ctx* c, Pipe& p, cudaStream_t s);
 // gather.cu

@@ -9,6 +9,8 @@
 // peer shard over NVLink (P2P load) or mapped host memory over PCIe (UVA zero-copy) are
 // all plain global addresses -- and writes them with 128-bit streaming stores.  The
 // reference runs one thread per float with a 64-bit divide and modulo per element.
+#include <stdlib.h>
+
 #include "context.h"
 
 namespace lgn {
@@ -16,9 +18,49 @@ namespace lgn {
 constexpr int GATHER_THREADS = 256;
 constexpr int GATHER_UNROLL = 4;
 
+// ---- row -> tier + address --------------------------------------------------------------
+// Three bindings (context.h: FeatView):
+//   identity  the whole table is resident in id order: no lookup at all.
+//   compact   lgn_place_compact: a 32-byte record per 96 nodes {repl_before, part_before, repl_bits[3], part_bits[3]}.  The
+//             map of a 111 M-node graph is 37 MB and stays in L2 (evict_last), where the int32 slot table (444 MB) costs one
+//             random DRAM access per gathered row -- measured 9 % of the whole step on the papers100M shape (DESIGN.md
+//             section 4).  Rows of a class are stored in node-id order: row = prefix + popcount.
+//   slot_of   int32[N] part*cap+row / -1 (the reference placement, hotness order inside the shards).
+// tier: 0 local shard, 1 peer shard, 2 base matrix (host).
+__device__ __forceinline__ const float* resolve_row(const FeatView& fv, long long nid, int dim, int& tier, unsigned long long keep)
+{
+    if (fv.identity) { tier = 0; return fv.shard_tab[fv.my_part] + nid * dim; }
+    if (fv.cmap) {
+        const uint32_t rec = (uint32_t)nid / (uint32_t)LGN_CMAP_NODES, j = (uint32_t)nid - rec * (uint32_t)LGN_CMAP_NODES;
+        const uint4 a = ld_stream_v4(fv.cmap + 2 * (size_t)rec, keep), b = ld_stream_v4(fv.cmap + 2 * (size_t)rec + 1, keep);
+        const uint32_t wi = j >> 5, bit = j & 31u, below = (1u << bit) - 1u;
+        const uint32_t rw = wi == 0 ? a.z : (wi == 1 ? a.w : b.x);
+        const uint32_t pw = wi == 0 ? b.y : (wi == 1 ? b.z : b.w);
+        if ((rw >> bit) & 1u) {
+            const uint32_t row = a.x + (wi > 0 ? __popc(a.z) : 0) + (wi > 1 ? __popc(a.w) : 0) + __popc(rw & below);
+            tier = 0;
+            return fv.shard_tab[fv.my_part] + (long long)row * dim;
+        }
+        if ((pw >> bit) & 1u) {
+            const uint32_t q = a.y + (wi > 0 ? __popc(b.y) : 0) + (wi > 1 ? __popc(b.z) : 0) + __popc(pw & below);
+            const uint32_t part = q % (uint32_t)fv.kg;
+            tier = (int)part == fv.my_part ? 0 : 1;
+            return fv.shard_tab[part] + (fv.n_repl + (long long)(q / (uint32_t)fv.kg)) * dim;
+        }
+        tier = 2;
+        return fv.base + nid * dim;
+    }
+    int32_t g = -1;
+    if (fv.slot_of) g = (int32_t)ld_nc_u32(fv.slot_of + nid);
+    if (g < 0) { tier = 2; return fv.base + nid * dim; }              // miss -> host / base matrix (Kernels.cu:692-696)
+    const int part = (int)(g / fv.cap);                               // hit -> shard[g / cap][g % cap] (Kernels.cu:697-699)
+    tier = part == fv.my_part ? 0 : 1;
+    return fv.shard_tab[part] + (g - part * fv.cap) * dim;
+}
+
 // VEC: 16-byte vectors per lane per row (1 covers D <= 128, 2 covers D <= 256, ...)
-template <int VEC>
-__global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
+template <int VEC, int UNR = GATHER_UNROLL>
+__global__ void __launch_bounds__(GATHER_THREADS, UNR == 2 ? 6 : 1) k_gather_v4(const __grid_constant__ FeatView fv, const int32_t* __restrict__ ids,
                                                               const int32_t* __restrict__ nc, int seg_slot, int n_segs,
                                                               float* __restrict__ out, int dim, long long n_nodes,
                                                               long long max_rows, BatchState* __restrict__ st)
@@ -32,9 +74,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_const
     const int nvec = dim >> 2;
     unsigned long long n_local = 0, n_peer = 0, n_host = 0;
     const unsigned long long stream_pol = policy_evict_first();   // rows are touched once: do not displace the dedup maps
+    const unsigned long long keep = policy_evict_last();
     // rows per warp-chunk: 32 for big segments, fewer for small ones so every warp gets work
     int chunk = (cnt + n_warps - 1) / n_warps;
-    chunk = chunk >= 32 ? 32 : (chunk <= GATHER_UNROLL ? GATHER_UNROLL : ((chunk + GATHER_UNROLL - 1) / GATHER_UNROLL) * GATHER_UNROLL);
+    chunk = chunk >= 32 ? 32 : (chunk <= UNR ? UNR : ((chunk + UNR - 1) / UNR) * UNR);
 
     for (int r0 = warp * chunk; r0 < cnt; r0 += n_warps * chunk) {
         // lane l: tier + source pointer of row r0+l
@@ -44,37 +87,30 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_v4(const __grid_const
             const int32_t id = (int32_t)ld_nc_u32(ids + off + r);
             if (id >= 0) {                                        // Kernels.cu:694
                 const long long nid = id < n_nodes ? id : id % n_nodes;
-                int32_t g = -1;
-                if (fv.slot_of) g = (int32_t)ld_nc_u32(fv.slot_of + nid);
-                if (g < 0) {                                      // miss -> host / base matrix (Kernels.cu:692-696)
-                    src = reinterpret_cast<const uint4*>(fv.base + nid * dim);
-                    n_host++;
-                } else {                                          // hit -> shard[g / cap][g % cap] (Kernels.cu:697-699)
-                    const int part = (int)(g / fv.cap);
-                    src = reinterpret_cast<const uint4*>(fv.shard_tab[part] + (g - part * fv.cap) * dim);
-                    if (part == fv.my_part) n_local++; else n_peer++;
-                }
+                int tier;
+                src = reinterpret_cast<const uint4*>(resolve_row(fv, nid, dim, tier, keep));
+                if (tier == 0) n_local++; else if (tier == 1) n_peer++; else n_host++;
             }
         } else if (lane < chunk && r < cnt) {
             st->status = LGN_E_CAPACITY;                          // reference: silent overflow (Server.cu:275)
         }
         const int rows = min(chunk, cnt - r0);
         uint4* dst0 = reinterpret_cast<uint4*>(out + (long long)(off + r0) * dim);
-        for (int rr = 0; rr < rows; rr += GATHER_UNROLL) {
-            uint4 v[GATHER_UNROLL][VEC];
-            const uint4* sp[GATHER_UNROLL];
+        for (int rr = 0; rr < rows; rr += UNR) {
+            uint4 v[UNR][VEC];
+            const uint4* sp[UNR];
 #pragma unroll
-            for (int u = 0; u < GATHER_UNROLL; u++) {
+            for (int u = 0; u < UNR; u++) {
                 sp[u] = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, (unsigned long long)src, (rr + u) & 31));
                 if (rr + u >= rows) sp[u] = nullptr;
             }
 #pragma unroll
-            for (int u = 0; u < GATHER_UNROLL; u++)
+            for (int u = 0; u < UNR; u++)
 #pragma unroll
                 for (int k = 0; k < VEC; k++)
                     if (sp[u] && lane + 32 * k < nvec) v[u][k] = ld_stream_v4(sp[u] + lane + 32 * k, stream_pol);
 #pragma unroll
-            for (int u = 0; u < GATHER_UNROLL; u++)
+            for (int u = 0; u < UNR; u++)
 #pragma unroll
                 for (int k = 0; k < VEC; k++)
                     if (sp[u] && lane + 32 * k < nvec) st_stream_v4(dst0 + (long long)(rr + u) * nvec + lane + 32 * k, v[u][k], stream_pol);
@@ -124,6 +160,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_con
 
     unsigned long long n_local = 0, n_peer = 0, n_host = 0;
     const unsigned long long stream_pol = policy_evict_first();
+    const unsigned long long keep = policy_evict_last();
     uint32_t phase = 0;
     const int stride = gridDim.x * blockDim.x;
     auto resolve = [&](int r) -> const float* {
@@ -132,12 +169,10 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_bulk(const __grid_con
         const int32_t id = (int32_t)ld_nc_u32(ids + off + r);
         if (id < 0) return nullptr;
         const long long nid = id < n_nodes ? id : id % n_nodes;
-        int32_t g = -1;
-        if (fv.slot_of) g = (int32_t)ld_nc_u32(fv.slot_of + nid);
-        if (g < 0) { n_host++; return fv.base + nid * dim; }
-        const int part = (int)(g / fv.cap);
-        if (part == fv.my_part) n_local++; else n_peer++;
-        return fv.shard_tab[part] + (g - part * fv.cap) * dim;
+        int tier;
+        const float* p = resolve_row(fv, nid, dim, tier, keep);
+        if (tier == 0) n_local++; else if (tier == 1) n_peer++; else n_host++;
+        return p;
     };
     int r = blockIdx.x * blockDim.x + t;
     const float* src = resolve(r);
@@ -198,11 +233,8 @@ __global__ void __launch_bounds__(GATHER_THREADS) k_gather_scalar(const __grid_c
         const int32_t id = ids[off + r];
         if (id < 0) continue;
         const long long nid = id < n_nodes ? id : id % n_nodes;
-        int32_t g = fv.slot_of ? fv.slot_of[nid] : -1;
-        const float* src;
         int tier;
-        if (g < 0) { src = fv.base + nid * dim; tier = 2; }
-        else { const int part = (int)(g / fv.cap); src = fv.shard_tab[part] + (g - part * fv.cap) * dim; tier = part == fv.my_part ? 0 : 1; }
+        const float* src = resolve_row(fv, nid, dim, tier, policy_evict_last());
         float* dst = out + (long long)(off + r) * dim;
         for (int k = lane; k < dim; k += 32) dst[k] = src[k];
         if (lane == 0) atomicAdd(&st->tier_rows[tier], 1ull);
@@ -287,7 +319,7 @@ static bool gather_vectorisable(const lgn_ctx* c, const Pipe& p)
 const char* gather_kernel_name(const lgn_ctx* c)
 {
     const Pipe& p = c->pipe[c->cur_pipe];
-    const int mode = c->gather_mode >= 0 ? c->gather_mode : (c->feat.n_parts > 1 ? 0 : 1);
+    const int mode = c->gather_mode >= 0 ? c->gather_mode : 0;
     if (!gather_vectorisable(c, p) || (c->cfg.feat_dim >> 2) > 128) return "k_gather_scalar";
     return mode == 1 ? "k_gather_bulk (cp.async.bulk feature extraction)" : "k_gather_v4 (128-bit LDG feature extraction)";
 }
@@ -298,19 +330,25 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
     const int dim = c->cfg.feat_dim;
     const int seg_slot = 3 + 2 * segment;
     const bool vec = gather_vectorisable(c, p);
-    const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 8));   // grid-stride over 32-row chunks; < 8 CTAs/SM leaves room for the sampler
+    // grid-stride over 32-row chunks.  2 CTAs/SM (16 warps x 4 rows in flight) already saturate HBM when two batches' gathers
+    // overlap and leave half of every SM's registers to the sampling chains of the other lanes: measured 0.097 ms/step against
+    // 0.104-0.107 with 3-8 CTAs/SM on the papers100M shape; peer rows (NVLink latency) want 3
+    const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 2));
     FeatView fv = c->feat;
     const int nvec = dim >> 2;
-    // auto: rows of peer shards cross NVLink with ~3 us latency -> the register-staged LDG variant with a
-    // smaller grid measured faster there; all-local caches use the bulk-copy (TMA) variant
-    const int mode = c->gather_mode >= 0 ? c->gather_mode : (c->feat.n_parts > 1 ? 0 : 1);
+    // default: the register-staged LDG variant.  Timed alone the bulk-copy (TMA) variant is as fast (both reach the copy
+    // peak with two launches overlapping), but with the sampling chains of the other lanes beside it the step takes
+    // 0.108 ms with the TMA gather and 0.097 ms with this one (papers100M shape, profiles/r02y_*); LGN_GATHER=bulk selects it
+    const int mode = c->gather_mode >= 0 ? c->gather_mode : 0;
     if (vec && mode == 1) {
         // staging rows + one mbarrier per thread; keep <= ~100 KB per CTA so two CTAs (or the sampler) fit beside it
         int threads = c->gather_threads;
         while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
         const size_t smem = (size_t)threads * (dim * 4 + 8);
         k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
-    } else if (vec && nvec <= 32)
+    } else if (vec && nvec <= 32 && c->gather_unroll == 2)
+        k_gather_v4<1, 2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+    else if (vec && nvec <= 32)
         k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 64)
         k_gather_v4<2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
@@ -324,6 +362,14 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
 void gather_init_device()
 {
     cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (const char* cv = getenv("LGN_CARVEOUT")) {      // experiment: one shared-memory carveout for every kernel of the pipeline
+        const int pct = atoi(cv);
+        cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_gather_v4<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_gather_v4<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_gather_v4<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        sampler_set_carveout(pct);
+    }
 }
 
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,

@@ -87,6 +87,75 @@ __global__ void k_widen(const uint32_t* __restrict__ in, unsigned long long* __r
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
+// ---- compact placement map (include/legion_b200.h: lgn_place_compact) ----
+// record r = 8 words: [0] replicated nodes before node r*96, [1] partitioned nodes before it, [2..4] replicated bits,
+// [5..7] partitioned bits of nodes r*96 .. r*96+95
+__global__ void k_cmap_mark(const int32_t* __restrict__ order, long long n_repl, long long n_cached, uint32_t* __restrict__ w)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cached; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t id = (uint32_t)order[i];
+        const uint32_t rec = id / (uint32_t)LGN_CMAP_NODES, j = id - rec * (uint32_t)LGN_CMAP_NODES;
+        atomicOr(&w[(size_t)rec * 8 + (i < n_repl ? 2 : 5) + (j >> 5)], 1u << (j & 31u));
+    }
+}
+__global__ void k_cmap_count(const uint32_t* __restrict__ w, long long n_rec, uint32_t* __restrict__ cnt_r, uint32_t* __restrict__ cnt_p)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (long long)gridDim.x * blockDim.x) {
+        const uint32_t* q = w + (size_t)r * 8;
+        cnt_r[r] = __popc(q[2]) + __popc(q[3]) + __popc(q[4]);
+        cnt_p[r] = __popc(q[5]) + __popc(q[6]) + __popc(q[7]);
+    }
+}
+__global__ void k_cmap_prefix(uint32_t* __restrict__ w, long long n_rec, const uint32_t* __restrict__ pre_r, const uint32_t* __restrict__ pre_p)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (long long)gridDim.x * blockDim.x) {
+        w[(size_t)r * 8] = pre_r[r];
+        w[(size_t)r * 8 + 1] = pre_p[r];
+    }
+}
+// shard j of the compact placement: one warp per 32 consecutive nodes, lane l classifies node base+l, the warp copies the
+// rows that belong to this shard.  Reads of the feature matrix and writes of the shard both advance in node-id order.
+__global__ void __launch_bounds__(256) k_cmap_fill(const uint32_t* __restrict__ w, long long n, long long n_repl, int kg, int part,
+                                                   const float* __restrict__ src, int dim, float* __restrict__ dst, long long cap)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (dim & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0;
+    for (long long n0 = warp * 32; n0 < n; n0 += n_warps * 32) {
+        const long long nid = n0 + lane;
+        long long row = -1;
+        if (nid < n) {
+            const uint32_t rec = (uint32_t)nid / (uint32_t)LGN_CMAP_NODES, j = (uint32_t)nid - rec * (uint32_t)LGN_CMAP_NODES;
+            const uint32_t* q = w + (size_t)rec * 8;
+            const uint32_t wi = j >> 5, bit = j & 31u, below = (1u << bit) - 1u;
+            if ((q[2 + wi] >> bit) & 1u) {
+                uint32_t c = q[0] + __popc(q[2 + wi] & below);
+                for (uint32_t k = 0; k < wi; k++) c += __popc(q[2 + k]);
+                row = c;
+            } else if ((q[5 + wi] >> bit) & 1u) {
+                uint32_t c = q[1] + __popc(q[5 + wi] & below);
+                for (uint32_t k = 0; k < wi; k++) c += __popc(q[5 + k]);
+                if ((int)(c % (uint32_t)kg) == part) row = n_repl + c / (uint32_t)kg;
+            }
+            if (row >= cap) row = -1;
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, row >= 0);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long r = __shfl_sync(0xffffffffu, row, l);
+            const float* s = src + (n0 + l) * dim;
+            float* d = dst + r * dim;
+            if (vec) {
+                for (int k = lane; k < (dim >> 2); k += 32) reinterpret_cast<uint4*>(d)[k] = ld_nc_v4(reinterpret_cast<const uint4*>(s) + k);
+            } else {
+                for (int k = lane; k < dim; k += 32) d[k] = s[k];
+            }
+        }
+    }
+}
+
 }  // namespace lgn
 
 using namespace lgn;
@@ -150,6 +219,48 @@ extern "C" int lgn_fill_feature_shard(const int32_t* order, int64_t n, int64_t c
                                       const float* features, int32_t dim, float* shard, void* stream)
 {
     return lgn_fill_feature_shard_hybrid(order, n, cap, kg, j, 0, features, dim, shard, stream);
+}
+
+extern "C" int64_t lgn_cmap_bytes(int64_t n_nodes)
+{
+    if (n_nodes <= 0) return 0;
+    return ((n_nodes + LGN_CMAP_NODES - 1) / LGN_CMAP_NODES) * 32;
+}
+
+extern "C" int lgn_place_compact(const int32_t* order, int64_t n, int64_t n_repl, int64_t n_part, void* cmap, void* stream)
+{
+    if (!order || !cmap || n <= 0 || n > 0x7fffffffLL || n_repl < 0 || n_part < 0 || n_repl + n_part > n) return LGN_E_ARG;
+    if ((uintptr_t)cmap & 15) return LGN_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_rec = (n + LGN_CMAP_NODES - 1) / LGN_CMAP_NODES;
+    uint32_t* w = (uint32_t*)cmap;
+    DevBuf cnt_r, cnt_p, pre_r, pre_p, tmp;
+    size_t tmp_bytes = 0;
+    CK(cnt_r.alloc(n_rec * 4)); CK(cnt_p.alloc(n_rec * 4)); CK(pre_r.alloc(n_rec * 4)); CK(pre_p.alloc(n_rec * 4));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt_r.as<uint32_t>(), pre_r.as<uint32_t>(), (int)n_rec, s));
+    CK(tmp.alloc(tmp_bytes));
+    CK(cudaMemsetAsync(w, 0, (size_t)n_rec * 32, s));
+    if (n_repl + n_part > 0) k_cmap_mark<<<1024, 256, 0, s>>>(order, n_repl, n_repl + n_part, w);
+    k_cmap_count<<<1024, 256, 0, s>>>(w, n_rec, cnt_r.as<uint32_t>(), cnt_p.as<uint32_t>());
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt_r.as<uint32_t>(), pre_r.as<uint32_t>(), (int)n_rec, s));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt_p.as<uint32_t>(), pre_p.as<uint32_t>(), (int)n_rec, s));
+    k_cmap_prefix<<<1024, 256, 0, s>>>(w, n_rec, pre_r.as<uint32_t>(), pre_p.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));          // the temporaries are released on return
+    return LGN_OK;
+}
+
+extern "C" int lgn_fill_feature_shard_compact(const void* cmap, int64_t n, int64_t n_repl, int32_t kg, int32_t j, const float* features,
+                                              int32_t dim, float* shard, int64_t cap, void* stream)
+{
+    if (!cmap || !features || !shard || n <= 0 || kg <= 0 || kg > LGN_MAX_PARTS || j < 0 || j >= kg || dim <= 0 || n_repl < 0 || cap < n_repl)
+        return LGN_E_ARG;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    k_cmap_fill<<<n_sm * 8, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)cmap, n, n_repl, kg, j, features, dim, shard, cap);
+    CK(cudaGetLastError());
+    return LGN_OK;
 }
 
 extern "C" int lgn_fill_topo_shard(const int32_t* order, int64_t n, int64_t cap, int32_t kg, int32_t j,

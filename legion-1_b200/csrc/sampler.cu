@@ -491,4 +491,17 @@ void launch_batch_end(lgn_ctx* c, cudaStream_t s, bool presc)
 
 int sample_items_per_tile() { return SAMPLE_ITEMS; }
 
+void sampler_set_carveout(int pct)
+{
+    cudaFuncSetAttribute(k_batch_begin, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_sample<LGN_RNG_MINSTD, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_sample<LGN_RNG_MINSTD, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_sample<LGN_RNG_PHILOX, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_sample<LGN_RNG_PHILOX, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_mark, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_assign, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_batch_end<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_batch_end<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 }  // namespace lgn

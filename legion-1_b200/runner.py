@@ -82,6 +82,15 @@ class Runner:
         a = (C.c_void_p * max(n, 1))(*[_ptr(x).value for x in shards])
         check(lib().lgn_bind_feature_cache(self.handle, n, a, _ptr(slot_of), C.c_int64(cap)), "lgn_bind_feature_cache")
 
+    def bind_feature_cache_compact(self, shards, cmap, n_repl, cap):
+        """shards addressed through a compact placement map (place_compact); cmap=None with ONE shard holding the whole
+        matrix in node-id order binds it directly (no lookup)."""
+        self._keep += [shards, cmap]
+        n = len(shards)
+        a = (C.c_void_p * max(n, 1))(*[_ptr(x).value for x in shards])
+        check(lib().lgn_bind_feature_cache_compact(self.handle, n, a, _ptr(cmap) if cmap is not None else None, C.c_int64(n_repl), C.c_int64(cap)),
+              "lgn_bind_feature_cache_compact")
+
     # ---- operators ----------------------------------------------------------------
     def batch_generate(self, mode, batch_size, counter, stream=None, pipe=None):
         """Batch_Generator::run (Operator.cu:10-32)."""
@@ -287,6 +296,22 @@ def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features, dim, stream=N
     shard = out if out is not None else DevArray.zeros((cap, dim), np.float32)
     check(lib().lgn_fill_feature_shard_hybrid(_ptr(order), C.c_int64(n), C.c_int64(cap), C.c_int32(kg), C.c_int32(j), C.c_int64(n_repl),
                                               _ptr(features), C.c_int32(dim), _ptr(shard), _vp(stream)), "lgn_fill_feature_shard_hybrid")
+    return shard
+
+
+def place_compact(order, n_repl, n_part, stream=None):
+    """B200 extension: compact, L2-resident placement map (lgn_place_compact): the n_repl hottest ranks replicated, the next
+    n_part partitioned, rows of a class in node-id order.  -> uint32[records * 8]"""
+    n = order.shape[0]
+    cmap = DevArray((int(lib().lgn_cmap_bytes(C.c_int64(n))) // 4,), np.uint32)
+    check(lib().lgn_place_compact(_ptr(order), C.c_int64(n), C.c_int64(n_repl), C.c_int64(n_part), _ptr(cmap), _vp(stream)), "lgn_place_compact")
+    return cmap
+
+
+def fill_feature_shard_compact(cmap, n, n_repl, kg, j, features, dim, cap, stream=None, out=None):
+    shard = out if out is not None else DevArray.zeros((cap, dim), np.float32)
+    check(lib().lgn_fill_feature_shard_compact(_ptr(cmap), C.c_int64(n), C.c_int64(n_repl), C.c_int32(kg), C.c_int32(j), _ptr(features),
+                                               C.c_int32(dim), _ptr(shard), C.c_int64(cap), _vp(stream)), "lgn_fill_feature_shard_compact")
     return shard
 
 

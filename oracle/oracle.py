@@ -181,6 +181,44 @@ def fill_feature_shard_hybrid(order, cap, kg, j, n_repl, features):
     return shard
 
 
+CMAP_NODES = 96
+
+
+def place_compact(order, n_repl, n_part, kg, my_part, cap):
+    """compact placement (include/legion_b200.h: lgn_place_compact), restated with numpy: classes by hotness rank
+    (GPUCache.cu:103-108 decides WHICH rows are cached), rows of a class in node-id order.
+    -> (record words uint32[records * 8], the equivalent int32 slot table part*cap+row / -1 of GPU my_part)"""
+    n = len(order)
+    is_r = np.zeros(n, bool)
+    is_p = np.zeros(n, bool)
+    is_r[order[:n_repl]] = True
+    is_p[order[n_repl:n_repl + n_part]] = True
+    rank_r = np.cumsum(is_r) - 1
+    q = np.cumsum(is_p) - 1
+    slot = np.full(n, -1, np.int64)
+    slot[is_r] = my_part * cap + rank_r[is_r]
+    slot[is_p] = (q[is_p] % kg) * cap + n_repl + q[is_p] // kg
+    n_rec = (n + CMAP_NODES - 1) // CMAP_NODES
+    pad = n_rec * CMAP_NODES - n
+    words = np.zeros((n_rec, 8), np.uint32)
+    for plane, col in ((is_r, 2), (is_p, 5)):
+        bits = np.concatenate([plane, np.zeros(pad, bool)]).reshape(n_rec, 3, 32)
+        words[:, col:col + 3] = (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=2).astype(np.uint32)
+        per_rec = bits.reshape(n_rec, 96).sum(axis=1)
+        words[:, 0 if col == 2 else 1] = (np.cumsum(per_rec) - per_rec).astype(np.uint32)
+    return words.reshape(-1), slot.astype(np.int32)
+
+
+def fill_feature_shard_compact(slot_of, cap, j, features):
+    """shard j of a placement given as a slot table (rows another GPU's table marks local for a replicated node are the
+    same rows on every GPU)."""
+    features = np.ascontiguousarray(features, np.float32)
+    shard = np.zeros((cap, features.shape[1]), np.float32)
+    mine = (slot_of >= 0) & (slot_of // cap == j)
+    shard[slot_of[mine] % cap] = features[mine]
+    return shard
+
+
 def fill_topo_shard(order, cap, kg, j, indptr, indices):
     ip = np.zeros(cap + 1, np.int64)
     n = lib().lgo_fill_topo_shard(_p(order), C.c_int64(len(order)), C.c_int64(cap), C.c_int32(kg), C.c_int32(j),

@@ -268,6 +268,71 @@ def test_hybrid_placement_gather(kg, frac_repl, frac_shard):
         r.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("gather", ["bulk", "ldg"])
+@pytest.mark.parametrize("dim,kg,frac_repl,frac_part", [(128, 4, 0.2, 0.5), (100, 1, 1.0, 0.0), (256, 8, 0.0, 1.0), (7, 2, 0.1, 0.2), (128, 2, 0.0, 0.0)])
+def test_compact_placement_gather(dim, kg, frac_repl, frac_part, gather, monkeypatch):
+    """compact (L2-resident) placement map: the map words, every shard and the gathered rows + tier counts of every emulated
+    GPU equal the numpy restatement; n_repl = N bound without a map (rows addressed by node id) gathers the same rows."""
+    import legion_b200 as L
+    from oracle import oracle as O
+    monkeypatch.setenv("LGN_GATHER", gather)
+    N = 20_011                                  # not a multiple of the 96-node record
+    d = L.synth.make_dataset(N, 10.0, dim, n_class=5)
+    rng = np.random.default_rng(2)
+    counts = rng.integers(0, 50, N).astype(np.uint32)
+    order_h = O.hot_order(counts)
+    order_d = L.hot_order(L.DevArray.from_numpy(counts))
+    n_repl = int(N * frac_repl)
+    n_part = min(N - n_repl, int(N * frac_part))
+    cap = max(1, n_repl + (n_part + kg - 1) // kg)
+    base = L.MappedHostArray.from_numpy(d.features)
+    cmap_d = L.place_compact(order_d, n_repl, n_part)
+    shards_d = [L.fill_feature_shard_compact(cmap_d, N, n_repl, kg, j, base, dim, cap) for j in range(kg)]
+    fanout, B = [10, 5], 512
+    smp = O.Sampler(d.indptr, d.indices, fanout, rng_mode=O.RNG_PHILOX, rng_seed=3)
+    seeds = d.train_ids[:B]
+    want = _oracle_batch(O, smp, seeds, 0)
+    total = int(want["nc"][0])
+    shards_h = None
+    for me in range(0, kg, max(1, kg // 2)):
+        words_h, slot_h = O.place_compact(order_h, n_repl, n_part, kg, me, cap)
+        assert np.array_equal(cmap_d.numpy(), words_h)
+        if shards_h is None:
+            shards_h = []
+            for j in range(kg):
+                _, slot_j = O.place_compact(order_h, n_repl, n_part, kg, j, cap)
+                shards_h.append(O.fill_feature_shard_compact(slot_j, cap, j, d.features))
+                assert np.array_equal(shards_d[j].numpy().view(np.uint32), shards_h[j].view(np.uint32))
+        r = L.Runner(N, dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=3, part=me)
+        r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+        r.bind_features(base)
+        r.bind_feature_cache_compact(shards_d, cmap_d, n_repl, cap)
+        r.batch_from_host(seeds, None, step=0)
+        r.run_batch(with_features=True)
+        got = r.fetch()
+        _assert_same(got, want)
+        assert np.array_equal(got["features"].view(np.uint32), d.features[want["sampled_ids"][:total]].view(np.uint32))
+        ref = np.zeros((total, dim), np.float32)
+        tiers = O.gather(want["sampled_ids"], 0, total, slot_h, cap, shards_h, d.features, ref, tiers=True)
+        assert np.array_equal(ref.view(np.uint32), got["features"].view(np.uint32))
+        assert r.tier_counts() == [int(tiers[me]), int(tiers[:kg].sum() - tiers[me]), int(tiers[kg])]
+        r.close()
+    if n_repl == N:      # the whole matrix resident in id order: no map
+        r = L.Runner(N, dim, B, fanout, rng_mode=L.RNG_PHILOX, rng_seed=3, part=0)
+        r.bind_topology(L.DevArray.from_numpy(d.indptr), L.DevArray.from_numpy(d.indices))
+        r.bind_features(base)
+        resident = L.DevArray.from_numpy(d.features)
+        assert np.array_equal(shards_d[0].numpy().view(np.uint32), d.features.view(np.uint32))    # id order IS the matrix
+        r.bind_feature_cache_compact([resident], None, N, N)
+        r.batch_from_host(seeds, None, step=0)
+        r.run_batch(with_features=True)
+        got = r.fetch()
+        assert np.array_equal(got["features"].view(np.uint32), d.features[want["sampled_ids"][:total]].view(np.uint32))
+        assert r.tier_counts() == [total, 0, 0]
+        r.close()
+
+
 @pytest.mark.parametrize("kg,budget_frac", [(1, 0.3), (2, 0.4), (8, 0.2), (8, 0.6), (4, 2.0)])
 def test_plan_hybrid_picks_the_cheapest_split(kg, budget_frac):
     """B200 placement model: of the 101 candidate splits (replicated / partitioned / host) the one with the smallest
@@ -576,7 +641,7 @@ def test_parity_suite_against_the_assert_build():
     if os.environ.get("LGN_LIBRARY"):
         pytest.skip("already running against an explicit library")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                          "sampling_bit_exact or edge_cases or full_neighbourhood or epoch or presampling or gather_bit_exact or run_batch"],
+                          "sampling_bit_exact or edge_cases or full_neighbourhood or epoch or presampling or gather_bit_exact or compact_placement or run_batch"],
                          env=dict(os.environ, LGN_LIBRARY=dbg), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout

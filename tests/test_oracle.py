@@ -216,6 +216,38 @@ def test_hotness_order_placement_and_gather(small):
     assert np.array_equal(ix[ip[t]:ip[t + 1]], d.indices[d.indptr[node]:d.indptr[node + 1]])
 
 
+@pytest.mark.parametrize("n,n_repl,n_part,kg", [(1000, 100, 400, 4), (96 * 7, 96 * 7, 0, 1), (5000, 0, 5000, 8), (777, 10, 20, 2), (97, 0, 0, 3)])
+def test_compact_placement_records_decode_to_the_slot_table(n, n_repl, n_part, kg):
+    """the record format of include/legion_b200.h (lgn_place_compact) decoded word by word, the way the gather kernel does
+    it (prefix + popcount), must give the slot table of the same placement; the cached SET is the hottest ranks."""
+    rng = np.random.default_rng(n)
+    order = O.hot_order(rng.integers(0, 9, n).astype(np.uint32))
+    cap = n_repl + (n_part + kg - 1) // kg + 1
+    me = kg - 1
+    words, slot = O.place_compact(order, n_repl, n_part, kg, me, cap)
+    w = words.reshape(-1, 8)
+    assert w.shape[0] == (n + 95) // 96
+    pc = lambda x: bin(int(x)).count("1")
+    for nid in range(n):
+        r, j = divmod(nid, 96)
+        wi, bit = j >> 5, j & 31
+        below = (1 << bit) - 1
+        want = -1
+        if (int(w[r, 2 + wi]) >> bit) & 1:
+            want = me * cap + int(w[r, 0]) + sum(pc(w[r, 2 + k]) for k in range(wi)) + pc(int(w[r, 2 + wi]) & below)
+        elif (int(w[r, 5 + wi]) >> bit) & 1:
+            q = int(w[r, 1]) + sum(pc(w[r, 5 + k]) for k in range(wi)) + pc(int(w[r, 5 + wi]) & below)
+            want = (q % kg) * cap + n_repl + q // kg
+        assert slot[nid] == want
+    cached = np.flatnonzero(slot >= 0)
+    assert set(cached.tolist()) == set(order[:n_repl + n_part].tolist())
+    # every (GPU, row) is used at most once, replicated rows are the same on every GPU
+    parts = slot[slot >= 0]
+    assert len(np.unique(parts)) == len(parts)
+    _, slot0 = O.place_compact(order, n_repl, n_part, kg, 0, cap)
+    assert np.array_equal(slot0[order[:n_repl]] % cap, slot[order[:n_repl]] % cap)
+
+
 def test_batch_generate_quirk():
     ids = np.arange(100, 137, dtype=np.int32)
     lab = ids % 5
