@@ -198,8 +198,6 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
     c->max_rows = cfg->max_feature_rows > 0 ? cfg->max_feature_rows : cap;
     c->n_lanes = cfg->n_lanes > 0 ? cfg->n_lanes : LGN_PIPELINE_DEPTH;
     CK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-    lgn::gather_init_device();
-    CK(cudaGetLastError());
     {   // dedup layout: a batch-sized hash table (L2-resident for any N) unless the direct map itself is small
         const char* dm = getenv("LGN_DEDUP");
         const bool small_map = (size_t)cfg->n_nodes * 4 <= ((size_t)32 << 20);   // measured: direct wins at 9.8 MB (C2), hash at 444 MB (C3)
@@ -306,6 +304,8 @@ static int create_impl(lgn_ctx* c, const lgn_config* cfg, long long cap, long lo
         c->shared_gather_stream = sg ? atoi(sg) : 0;
     }
     c->feat.my_part = cfg->part;
+    lgn::gather_init_device(c);
+    CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     return LGN_OK;
 }

@@ -128,7 +128,7 @@ void sampler_set_carveout(int pct);
 void reset_dedup(lgn_ctx* c, Pipe& p, cudaStream_t s);
 // gather.cu
 void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs);
-void gather_init_device();
+void gather_init_device(const lgn_ctx* c);
 const char* gather_kernel_name(const lgn_ctx* c);
 void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_rows, long long rows_per_shard, bool peers_only, uint32_t salt);
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,

@@ -308,6 +308,8 @@ void launch_debug_shard_read(lgn_ctx* c, cudaStream_t s, int pipe, long long n_r
     k_debug_shard_read<<<c->n_sm * 3, GATHER_THREADS, 0, s>>>(tb, rows_per_shard, n_rows, c->cfg.feat_dim, c->pipe[pipe].features, salt);
 }
 
+static int gather_auto_mode(const lgn_ctx* c);
+
 static bool gather_vectorisable(const lgn_ctx* c, const Pipe& p)
 {
     const int dim = c->cfg.feat_dim;
@@ -319,7 +321,7 @@ static bool gather_vectorisable(const lgn_ctx* c, const Pipe& p)
 const char* gather_kernel_name(const lgn_ctx* c)
 {
     const Pipe& p = c->pipe[c->cur_pipe];
-    const int mode = c->gather_mode >= 0 ? c->gather_mode : 0;
+    const int mode = gather_auto_mode(c);
     if (!gather_vectorisable(c, p) || (c->cfg.feat_dim >> 2) > 128) return "k_gather_scalar";
     return mode == 1 ? "k_gather_bulk (cp.async.bulk feature extraction)" : "k_gather_v4 (128-bit LDG feature extraction)";
 }
@@ -336,17 +338,19 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
     const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 2));
     FeatView fv = c->feat;
     const int nvec = dim >> 2;
-    // default: the register-staged LDG variant.  Timed alone the bulk-copy (TMA) variant is as fast (both reach the copy
-    // peak with two launches overlapping), but with the sampling chains of the other lanes beside it the step takes
-    // 0.108 ms with the TMA gather and 0.097 ms with this one (papers100M shape, profiles/r02y_*); LGN_GATHER=bulk selects it
-    const int mode = c->gather_mode >= 0 ? c->gather_mode : 0;
+    // Timed alone the two variants are equally fast (both reach the copy peak with two launches overlapping); with the
+    // sampling chains of the other lanes beside them the LDG variant wins on 512-byte rows (0.097 vs 0.099 ms/step), the
+    // bulk-copy variant on 400-byte rows (0.095 vs 0.100): gather_auto_mode
+    const int mode = gather_auto_mode(c);
     if (vec && mode == 1) {
         // staging rows + one mbarrier per thread; keep <= ~100 KB per CTA so two CTAs (or the sampler) fit beside it
         int threads = c->gather_threads;
         while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
         const size_t smem = (size_t)threads * (dim * 4 + 8);
         k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
-    } else if (vec && nvec <= 32 && c->gather_unroll == 2)
+    } else if (vec && nvec <= 32 && c->gather_unroll == 8)
+        k_gather_v4<1, 8><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
+    else if (vec && nvec <= 32 && c->gather_unroll == 2)
         k_gather_v4<1, 2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 32)
         k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
@@ -358,18 +362,38 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
         k_gather_scalar<<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
 }
 
+// gather variant of a context when LGN_GATHER does not force one (measured on one B200, 4 batches in flight):
+// rows that fill whole 512-byte warp transactions (D % 128 == 0) and every cache with peer shards take the register-staged
+// LDG variant; other row sizes (products' 400-byte rows leave 7 of 32 lanes idle) take the bulk-copy (TMA) variant
+static int gather_auto_mode(const lgn_ctx* c)
+{
+    if (c->gather_mode >= 0) return c->gather_mode;
+    return (c->feat.n_parts > 1 || (c->cfg.feat_dim & 127) == 0) ? 0 : 1;
+}
+
+static void set_carveout_all(int pct)
+{
+    cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_v4<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_v4<1, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_v4<1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_v4<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_v4<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_gather_scalar, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    sampler_set_carveout(pct);
+}
+
 // per-device function attributes (a process may drive several GPUs): called once per context from lgn_create
-void gather_init_device()
+void gather_init_device(const lgn_ctx* c)
 {
     cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (const char* cv = getenv("LGN_CARVEOUT")) {      // experiment: one shared-memory carveout for every kernel of the pipeline
-        const int pct = atoi(cv);
-        cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_gather_v4<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_gather_v4<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_gather_v4<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        sampler_set_carveout(pct);
-    }
+    // LGN_CARVEOUT=<percent>: ONE shared-memory / L1 split for every kernel of the pipeline (experiment knob).  The bulk-copy
+    // gather needs ~100 KB of shared memory per CTA, the sampling kernels a few KB; with the driver's per-kernel choice the
+    // papers100M step takes 0.1085 ms with the bulk-copy gather, 0.0995 with a common 50 % split (profiles/r02aa_mix_sweep.txt),
+    // but products' 400-byte rows lose 3 % with it -- so it stays a knob; the default gather for 512-byte rows (LDG) uses no
+    // shared memory at all.
+    (void)c;
+    if (const char* cv = getenv("LGN_CARVEOUT")) set_carveout_all(atoi(cv));
 }
 
 void launch_row_copy(const int32_t* order, long long n, long long cap, int kg, int j, long long n_repl, const float* src, int dim,

@@ -9,6 +9,8 @@ run C3 LGN_RESOLVE_CTAS=16
 run C3 LGN_SAMPLE_CTAS=8
 run C3 LGN_END_CTAS=2
 run C3 LGN_GATHER_LDG_CTAS=3
+run C3 LGN_GATHER_LDG_CTAS=1 LGN_GATHER_UNROLL=8
+run C3 LGN_GATHER_LDG_CTAS=2 LGN_GATHER_UNROLL=8
 run C2 LGN_X=0
 run C2 LGN_GATHER=bulk
 run C2 LGN_GATHER_LDG_CTAS=3
