@@ -596,6 +596,8 @@ def run_b200(args):
         cached_rows = min(N, c.n_repl + (c.cap - c.n_repl) * c.kg_bind)
         c.compact = args.slot_map == "compact"
         c.identity = c.compact and c.kg_bind == 1 and cached_rows >= N       # whole table resident: rows addressed by node id
+        if os.environ.get("LGN_BENCH_NO_IDENTITY"):                         # experiment: go through the placement map anyway
+            c.identity = False
         if c.identity:
             c.slot_of = None
         elif c.compact:

@@ -333,9 +333,10 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
     const int seg_slot = 3 + 2 * segment;
     const bool vec = gather_vectorisable(c, p);
     // grid-stride over 32-row chunks.  2 CTAs/SM (16 warps x 4 rows in flight) already saturate HBM when two batches' gathers
-    // overlap and leave half of every SM's registers to the sampling chains of the other lanes: measured 0.097 ms/step against
-    // 0.104-0.107 with 3-8 CTAs/SM on the papers100M shape; peer rows (NVLink latency) want 3
-    const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : (c->feat.n_parts > 1 ? 3 : 2));
+    // overlap and leave half of every SM's registers to the sampling chains of the other lanes: papers100M shape, one GPU
+    // 0.097 ms/step against 0.104-0.107 with 3-8 CTAs/SM; two GPUs, half of the rows over NVLink 0.177 against 0.191 (3) and
+    // 0.183 (4) (profiles/r02aa_mix_sweep.txt, r02af_n2_ldg_ctas.txt)
+    const int blocks = c->n_sm * (c->gather_ldg_ctas > 0 ? c->gather_ldg_ctas : 2);
     FeatView fv = c->feat;
     const int nvec = dim >> 2;
     // Timed alone the two variants are equally fast (both reach the copy peak with two launches overlapping); with the
