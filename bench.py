@@ -601,8 +601,12 @@ def run_b200(args):
         if c.identity:
             c.slot_of = None
         elif c.compact:
-            c.slot_of = L.place_compact(order, min(c.n_repl, N), cached_rows - min(c.n_repl, N), stream=sp)
-        else:
+            try:
+                c.slot_of = L.place_compact(order, *cluster.compact_split(N, c.n_repl, c.cap, c.kg_bind), stream=sp)
+            except L.LegionError as e:       # argument validation only (identical on every rank): fall back to the int32 table, say so
+                log(f"rank {rank}: compact placement refused ({e}); using the int32 slot table")
+                c.compact = False
+        if not c.identity and not c.compact:
             c.slot_of = L.place_hybrid(order, c.cap, c.kg_bind, c.n_repl, part_bind)
         base = ds.features
         if cached_rows < N:       # misses: pinned host memory over UVA (only then is the 4*N*D-byte host copy made)

@@ -139,3 +139,13 @@ def shard_ranks(cap, kg, j, n):
 
 def capacity_for(n_cached, kg):
     return max(1, (int(n_cached) + kg - 1) // kg)
+
+
+def compact_split(n_nodes, n_repl, cap, kg):
+    """rows of the compact placement (lgn_place_compact) for a shard height `cap`: -> (n_repl, n_part) with the n_repl hottest
+    ranks replicated on every GPU and the next n_part dealt over kg GPUs (rank q of the class -> GPU q % kg, row n_repl + q // kg)."""
+    n_repl = min(int(n_repl), int(n_nodes))
+    cached = min(int(n_nodes), n_repl + (int(cap) - n_repl) * int(kg))
+    n_part = max(0, cached - n_repl)
+    assert int(cap) >= n_repl + (n_part + kg - 1) // kg, "shard too low for the partitioned class"
+    return n_repl, n_part

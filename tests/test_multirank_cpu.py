@@ -73,6 +73,23 @@ def _worker(rank, world, port, q):
         tiers = O.gather(batch["sampled_ids"], 0, total, slot, cap, shards, d.features, out, tiers=True)
         assert np.array_equal(out.view(np.uint32), d.features[batch["sampled_ids"][:total]].view(np.uint32))
         assert tiers[:world].sum() > 0 and tiers.sum() == total
+        # compact placement (lgn_place_compact): the map is the same on every rank, replicated rows are local everywhere,
+        # partitioned rows live on exactly one rank; every rank gathers the same bit-exact rows through its own slot view
+        n_repl_c, cap_c = 1_000, 1_000 + cluster.capacity_for(2_500, world)
+        n_repl_c, n_part_c = cluster.compact_split(d.n_nodes, n_repl_c, cap_c, world)
+        assert (n_repl_c, n_part_c) == (1_000, 2_500 + (2_500 % world))
+        words, slot_c = O.place_compact(order, n_repl_c, n_part_c, world, rank, cap_c)
+        all_words = [None] * world
+        dist.all_gather_object(all_words, words.tobytes())
+        assert all(w == all_words[0] for w in all_words)
+        shard_c = O.fill_feature_shard_compact(slot_c, cap_c, rank, d.features)
+        shards_c = [None] * world
+        dist.all_gather_object(shards_c, shard_c)
+        out_c = np.zeros((total, d.dim), np.float32)
+        tiers_c = O.gather(batch["sampled_ids"], 0, total, slot_c, cap_c, shards_c, d.features, out_c, tiers=True)
+        assert np.array_equal(out_c.view(np.uint32), d.features[batch["sampled_ids"][:total]].view(np.uint32))
+        hot = np.isin(batch["sampled_ids"][:total], order[:n_repl_c]).sum()
+        assert tiers_c[rank] >= hot and tiers_c.sum() == total
         q.put((rank, "ok"))
     except Exception as e:      # noqa: BLE001
         import traceback
