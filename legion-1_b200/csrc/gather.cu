@@ -3,8 +3,9 @@
 // Replaces zero_copy_with_aggregated_cache (Kernels.cu:662-702), the cuckoo lookup of
 // FindFeat (GPUCache.cu:387-432, bght::bcht::find) and FeatFillUp (GPUCache.cu:200-205).
 //
-// One warp owns 32 consecutive output rows: lane l resolves row l's tier (direct-mapped
-// int32 slot table: one 4-byte read instead of up to three 128-byte cuckoo buckets), the
+// One warp owns 32 consecutive output rows: lane l resolves row l's tier (resolve_row: no
+// lookup at all for a resident table, a 32-byte compact-map record, or a direct-mapped int32
+// slot table -- instead of up to three 128-byte cuckoo buckets), the
 // warp then streams the rows UNROLL at a time with 128-bit loads -- local HBM shard,
 // peer shard over NVLink (P2P load) or mapped host memory over PCIe (UVA zero-copy) are
 // all plain global addresses -- and writes them with 128-bit streaming stores.  The
@@ -349,9 +350,7 @@ void launch_gather(lgn_ctx* c, cudaStream_t s, int segment, int n_segs)
         while (threads > 32 && (size_t)threads * (dim * 4 + 8) > 100 * 1024) threads -= 32;
         const size_t smem = (size_t)threads * (dim * 4 + 8);
         k_gather_bulk<<<c->n_sm * c->gather_ctas_per_sm, threads, smem, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
-    } else if (vec && nvec <= 32 && c->gather_unroll == 8)
-        k_gather_v4<1, 8><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
-    else if (vec && nvec <= 32 && c->gather_unroll == 2)
+    } else if (vec && nvec <= 32 && c->gather_unroll == 2)      // experiment knob: 2 rows in flight per warp, 40 registers (slower: r02y)
         k_gather_v4<1, 2><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
     else if (vec && nvec <= 32)
         k_gather_v4<1><<<blocks, GATHER_THREADS, 0, s>>>(fv, p.ids, p.nc, seg_slot, n_segs, p.features, dim, c->cfg.n_nodes, c->max_rows, p.state);
@@ -377,7 +376,6 @@ static void set_carveout_all(int pct)
     cudaFuncSetAttribute(k_gather_bulk, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_gather_v4<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_gather_v4<1, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(k_gather_v4<1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_gather_v4<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_gather_v4<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(k_gather_scalar, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
