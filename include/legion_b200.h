@@ -170,8 +170,9 @@ const char* lgn_gather_kernel_name(const lgn_ctx* ctx);
 int lgn_finish_batch(lgn_ctx* ctx, void* stream, int32_t is_presc);
 /* the whole GPURunner::RunOnce / RunPreSc DAG (Server.cu:284-328) of the selected slot: sampling on `stream`, feature
  * extraction on the slot's own low-priority stream, event-chained per hop.  Replayed as a CUDA graph from the second
- * call on.  `stream` is NOT joined with the gather stream at the end: the next batch's sampling overlaps this
- * batch's gathers.  A slot's batch is complete when its event fires:
+ * call on.  Issued eagerly, `stream` is NOT joined with the gather stream at the end; the captured form has to
+ * rejoin it (a capture must end on its origin stream), so drive every slot from its own stream: the sampling
+ * chains of the other slots then run under this batch's gathers.  A slot's batch is complete when its event fires:
  * lgn_wait_pipe makes `stream` wait for it (device side), lgn_sync_pipe blocks the host
  * (the reference's busy-poll on the last operator event, Server.cu:318-323). */
 int lgn_run_batch(lgn_ctx* ctx, void* stream, int32_t with_features, int32_t is_presc);
